@@ -1,0 +1,60 @@
+"""ctypes binding of libxclip_b200.so - the only way Python reaches the CUDA kernels.
+
+There is deliberately no fallback: if the shared library is missing, or a call
+returns a non-zero code, this raises.  Signatures mirror include/xclip_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_void_p
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libxclip_b200.so"
+
+_lib = None
+
+
+class XClipB200Error(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes).  Kept in one table so tests can check that every
+# symbol declared in include/xclip_b200.h is exported and bound.
+SIGNATURES = {
+    "xclip_abi_version": (c_int, []),
+    "xclip_last_error": (c_char_p, []),
+    "xclip_init": (c_int, []),
+    "xclip_launch_count": (c_longlong, []),
+    "xclip_launch_count_reset": (None, []),
+    "xclip_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
+                                c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                c_int64, c_int, c_int, c_void_p]),
+}
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise XClipB200Error(
+            f"{LIB_PATH} is missing. Build it with `python -m x_clip_b200.build` "
+            "(nvcc, sm_100a). x_clip_b200 has no CPU or eager-PyTorch fallback.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().xclip_last_error()
+        raise XClipB200Error(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,287 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = alpha * A * B^T (+ bias[N]) (+ residual[M,N])        bf16 x bf16 -> fp32 accum
+//
+// Operand storage (both cases are fed straight from global memory by TMA, no transposes):
+//   a_major = K  : A is [M,K] row-major (K contiguous)          - activations in fwd / dgrad
+//   a_major = MN : A is given as At[K,M] row-major (M contiguous)- dY^T in wgrad
+//   b_major = K  : B is [N,K] row-major                          - nn.Linear weight [out,in] in fwd
+//   b_major = MN : B is given as Bt[K,N] row-major (N contiguous)- weight in dgrad, X in wgrad
+//
+// This one kernel covers the reference's nn.Linear call sites on the hot path
+// (x_clip/x_clip.py:191,195,209,210,358,368,556,570) and their autograd backward.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warps 0-3 : epilogue  (TMEM -> registers -> global; warp w owns TMEM lanes 32w..32w+31)
+//   warp  4   : TMA producer (one elected lane)
+//   warp  5   : TMEM allocator + MMA issuer (one lane issues tcgen05.mma / tcgen05.commit)
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulators double-buffered
+// full/empty (MMA <-> epilogue), static persistent tile scheduler with optional split-K.
+#pragma once
+
+#include "common.cuh"
+
+namespace xclip {
+
+struct GemmParams {
+  int M, N, K;
+  void* c;
+  long long ldc;
+  int c_is_f32;        // 0: bf16 out, 1: fp32 out
+  int atomic_add;      // fp32 out only: red.add into C (required when split_k > 1)
+  int split_k;
+  float alpha;
+  const float* bias;   // [N] or null
+  const bf16* residual;  // bf16 [*, N] or null
+  long long ldr;
+  int res_row_mod;     // residual row = row % res_row_mod when > 0 (positional tables)
+};
+
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KiB
+  static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;      // 16/32 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + align slack
+};
+
+template <int BLOCK_N, int A_MAJOR, int B_MAJOR>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using S = GemmSmem<BLOCK_N>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator
+  static_assert(kTmemCols == 256 || kTmemCols == 512, "BLOCK_N must be 128 or 256");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_kb = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+  const int splits = p.split_k > 0 ? p.split_k : 1;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  const int num_tiles = num_m * num_n * splits;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t % num_n;
+        const int m_blk = (t / num_n) % num_m;
+        const int split = t / (num_n * num_m);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          uint8_t* sa = smem_a + stage * S::kABytes;
+          uint8_t* sb = smem_b + stage * S::kBBytes;
+          if (A_MAJOR == kMajorK) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM);
+          } else {
+#pragma unroll
+            for (int g = 0; g < kGemmBlockM / 64; ++g)
+              tma_load_2d(sa + g * (kGemmBlockK * 128), &tmA, &full_bar[stage],
+                          m_blk * kGemmBlockM + g * 64, kb * kGemmBlockK);
+          }
+          if (B_MAJOR == kMajorK) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBlockK, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BLOCK_N / 64; ++g)
+              tma_load_2d(sb + g * (kGemmBlockK * 128), &tmB, &full_bar[stage],
+                          n_blk * BLOCK_N + g * 64, kb * kGemmBlockK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
+    // K-major: SBO = 1024 (8 rows x 128 B), LBO unused.  MN-major: SBO = 1024 between
+    // 8-row K groups, LBO = BLOCK_K*128 between 64-wide M/N groups (one TMA box each).
+    constexpr uint32_t kLboMN = kGemmBlockK * 128;
+    constexpr uint32_t kAStep = (A_MAJOR == kMajorK) ? 32u : 2048u;  // bytes per UMMA_K=16
+    constexpr uint32_t kBStep = (B_MAJOR == kMajorK) ? 32u : 2048u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int split = t / (num_n * num_m);
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, num_kb);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+          const uint64_t adesc =
+              make_smem_desc(a_addr, A_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
+          const uint64_t bdesc =
+              make_smem_desc(b_addr, B_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            umma_bf16(tmem_d, desc_advance(adesc, k * kAStep), desc_advance(bdesc, k * kBStep),
+                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3) =====================
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int n_blk = t % num_n;
+      const int m_blk = (t / num_n) % num_m;
+      const int split = t / (num_n * num_m);
+      const int kb0 = split * kb_per_split;
+      const bool has_k = kb0 < min(kb0 + kb_per_split, num_kb);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (!has_k) continue;  // (cannot happen: host clamps split_k) keeps roles in lock-step
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+
+      const int row = m_blk * kGemmBlockM + warp * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BLOCK_N;
+      const bf16* res_row = nullptr;
+      if (p.residual != nullptr && row_ok) {
+        const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+        res_row = p.residual + rr * p.ldr;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (row_ok && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          if (p.bias != nullptr && split == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N) {
+                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
+            }
+          }
+          if (res_row != nullptr && split == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (col0 + i < p.N) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
+                float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
+                float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+                f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
+                f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
+              }
+            }
+          }
+          if (p.c_is_f32) {
+            float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+            if (p.atomic_add) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (col0 + i < p.N) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i),
+                               "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
+                               : "memory");
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (col0 + i < p.N)
+                  *reinterpret_cast<float4*>(crow + i) =
+                      make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              }
+            }
+          } else {
+            bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (col0 + i < p.N) {
+                uint4 o;
+                o.x = pack_bf16x2(f[i], f[i + 1]);
+                o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+                o.z = pack_bf16x2(f[i + 4], f[i + 5]);
+                o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                *reinterpret_cast<uint4*>(crow + i) = o;
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace xclip
