@@ -64,6 +64,74 @@ int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const void* b, int6
                     float alpha, const float* bias, const void* residual, int64_t ldr,
                     int res_row_mod, int accumulate, xclip_stream_t stream);
 
+/* ---- row-wise kernels ---------------------------------------------------
+ * Gain-only LayerNorm, biased variance (x_clip/x_clip.py:112-121).  One call can also apply
+ * the residual add of the block (:288) and the NEXT pre-norm (:126) so the row is read once:
+ *   out  = LN(x) * g (+ res)                      stats  = (mean, rstd) of x        [rows,2] f32
+ *   out2 = LN(bf16(out)) * g2   (if g2 != NULL)   stats2 = (mean, rstd) of bf16(out)
+ * x/res/out/out2 bf16 [rows, d]; g/g2 f32 [d]; d in 256*{1,2,3,4}.  eps: the reference uses
+ * 1e-5 for fp32 activations and 1e-3 otherwise (:118) - the caller chooses. */
+int xclip_layernorm_fwd(const void* x, int64_t ldx, const float* g, const void* res,
+                        int64_t ldres, void* out, int64_t ldo, float* stats, const float* g2,
+                        void* out2, int64_t ldo2, float* stats2, int rows, int d, float eps,
+                        xclip_stream_t stream);
+/* dx = dLN(dy; x, stats, g) (+ add);  dg += sum_rows dy * xhat   (dg f32 [d], accumulated) */
+int xclip_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                        const float* stats, const float* g, const void* add, int64_t ldadd,
+                        void* dx, int64_t lddx, float* dg, int rows, int d,
+                        xclip_stream_t stream);
+/* GEGLU + LayerNorm of FeedForward (x_clip/x_clip.py:180-183,:193): u = [value | gate] bf16
+ * [rows, 2*dh]; h = LN(value * gelu_erf(gate)) * g, bf16 [rows, dh]; dh in 1024*{1,2,3,4}. */
+int xclip_geglu_ln_fwd(const void* u, int64_t ldu, const float* g, void* h, int64_t ldh,
+                       float* stats, int rows, int dh, float eps, xclip_stream_t stream);
+int xclip_geglu_ln_bwd(const void* dh_grad, int64_t lddh, const void* u, int64_t ldu,
+                       const float* stats, const float* g, void* du, int64_t lddu, float* dg,
+                       int rows, int dh, xclip_stream_t stream);
+/* l2norm = F.normalize(dim=-1, eps=1e-12) (x_clip/x_clip.py:54-55, used at :715,:724).
+ * p f32 [rows,d] -> z f32, z16 bf16 (MMA operand of the logits), inv = 1/max(|p|,eps). */
+int xclip_l2norm_fwd(const float* p, int64_t ldp, float* z, void* z16, float* inv, int rows,
+                     int d, xclip_stream_t stream);
+/* dp (bf16) = inv * (dz - z <z,dz>) */
+int xclip_l2norm_bwd(const float* dz, const float* z, const float* inv, void* dp, int rows, int d,
+                     xclip_stream_t stream);
+int xclip_cast_f32_bf16(const float* src, void* dst, int64_t n, xclip_stream_t stream);
+
+/* ---- fused attention (tcgen05) -------------------------------------------
+ * Attention core of x_clip/x_clip.py:217-244 (dim_head = 64, n <= 384, non-causal):
+ * qkv bf16 [B*n, ld_qkv] holds q | k | v, each heads*64 wide, head-major inside.
+ * key_mask uint8 [B, n] (1 = attend; may be NULL).  o bf16 [B*n, ldo] (heads merged).
+ * lse f32 [B, heads, n]: base-2 log-sum-exp of scale*log2(e)*scores (saved for backward). */
+int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o, int64_t ldo,
+                   float* lse, int B, int n, int heads, float scale, xclip_stream_t stream);
+/* delta f32 [B, heads, n] is scratch (rowsum(dO*O), written here).  dq_workspace f32
+ * [B*n, heads*64] is required when n > 128 (partial dQ across key tiles), else may be NULL. */
+int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, const void* o,
+                   int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta,
+                   void* dqkv, int64_t ld_dqkv, float* dq_workspace, int B, int n, int heads,
+                   float scale, xclip_stream_t stream);
+
+/* ---- similarity + InfoNCE / DCL (tcgen05, logits never materialised in forward) ----------
+ * Replaces x_clip/x_clip.py:813-847 for one direction of the loss:
+ *   s[r,c] = temp_exp * <a_r, b_c>,  a bf16 [R,D] = LOCAL unit-norm latents of one modality,
+ *   b bf16 [C,D] = ALL latents of the other modality; the positive of row r is column
+ *   r + diag_offset.  dcl != 0 removes the positive from the denominator (:834-836).
+ * fwd:  lse[r] = log sum_c exp(s[r,c]);  pos[r] = s[r, r+diag_offset];
+ *       *loss_accum += loss_scale * sum_r (lse[r] - pos[r])     (loss_accum may be NULL)
+ *       part_ws: f32 scratch [xclip_nce_num_col_blocks(C) * R].
+ *       (the reference's +1e-20 inside its logs, :51-52, is below fp32 resolution here)
+ * bwd:  g[r,c] = w_row*exp(s - lse_row[r]) + w_col*exp(s - lse_col[c]) - w_diag*[c == r+diag]
+ *       (exp terms skipped on the positive when dcl), written bf16 [R, ldg>=roundup8(C)];
+ *       *dtemp += sum g*s (d loss / d temperature parameter) when dtemp != NULL.
+ *       The latent gradient is then  dA = temp_exp * g @ b  via xclip_gemm_bf16. */
+int xclip_nce_num_col_blocks(int C);
+int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D, float temp_exp,
+                  int diag_offset, int dcl, float* part_ws, float* pos, float* lse,
+                  float* loss_accum, float loss_scale, xclip_stream_t stream);
+int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, float temp_exp,
+                  int diag_offset, int dcl, const float* lse_row, const float* lse_col,
+                  float w_row, float w_col, float w_diag, void* g, int64_t ldg, float* dtemp,
+                  xclip_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,65 @@
+"""Fused attention fwd/bwd vs an fp32 torch restatement of the reference core
+(x_clip/x_clip.py:217-244) on the same bf16-rounded q,k,v."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_attention(qkv, mask, B, n, H, scale):
+    q, k, v = qkv.float().view(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q * scale) @ k.transpose(-1, -2)
+    if mask is not None:
+        s = s.masked_fill(~mask[:, None, None, :], -torch.finfo(torch.float32).max)
+    p = s.softmax(-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * n, H * 64), s
+
+
+CASES = [(2, 33, 4, False), (3, 65, 8, False), (2, 128, 2, True), (2, 17, 4, True),
+         (2, 197, 12, False), (2, 257, 8, True), (1, 384, 2, True), (5, 78, 8, True)]
+
+
+def _mk(B, n, H, masked, dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    qkv = torch.randn(B * n, 3 * H * 64, generator=g).to(dev).bfloat16()
+    mask = None
+    if masked:
+        mask = (torch.rand(B, n, generator=g) > 0.3).to(dev)
+        mask[:, 0] = True     # the CLS key is always attendable (x_clip.py:335)
+    return qkv, mask
+
+
+@pytest.mark.parametrize("B,n,H,masked", CASES)
+def test_attn_fwd(cuda_device, B, n, H, masked):
+    from x_clip_b200 import kernels as K
+    qkv, mask = _mk(B, n, H, masked, cuda_device)
+    scale = 64 ** -0.5
+    o, lse = K.attn_fwd(qkv, mask, B, n, H, scale)
+    torch.cuda.synchronize()
+    ref, s = _ref_attention(qkv, mask, B, n, H, scale)
+    err = (o.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), f"o err {err}"
+    ref_lse = torch.logsumexp(s, dim=-1) / 0.6931471805599453
+    assert torch.allclose(lse, ref_lse, atol=2e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("B,n,H,masked", CASES)
+def test_attn_bwd(cuda_device, B, n, H, masked):
+    from x_clip_b200 import kernels as K
+    qkv, mask = _mk(B, n, H, masked, cuda_device, seed=1)
+    scale = 64 ** -0.5
+    o, lse = K.attn_fwd(qkv, mask, B, n, H, scale)
+    d_o = torch.randn(B * n, H * 64, device=cuda_device).bfloat16()
+    dqkv = K.attn_bwd(qkv, mask, o, d_o, lse, B, n, H, scale)
+    torch.cuda.synchronize()
+    qf = qkv.float().requires_grad_(True)
+    ref, _ = _ref_attention(qf, mask, B, n, H, scale)
+    ref.backward(d_o.float())
+    g = qf.grad
+    inner = H * 64
+    for name, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
+        err = (dqkv[:, sl].float() - g[:, sl]).abs().max().item()
+        sc = g[:, sl].abs().max().item()
+        assert err <= 3e-2 * sc, f"{name}: err {err} vs scale {sc}"
+        rel = (dqkv[:, sl].float() - g[:, sl]).norm().item() / g[:, sl].norm().item()
+        assert rel < 1e-2, f"{name}: rel fro err {rel}"

@@ -1,0 +1,390 @@
+// Fused multi-head attention backward (dim_head = 64, n <= 384), sm_100a tcgen05.
+//
+// Backward of the reference's Attention core (x_clip/x_clip.py:217-244) as produced by
+// autograd over einsum/softmax/einsum; scores are recomputed on-chip from Q,K and the saved
+// per-row log-sum-exp, never read from HBM.
+//
+// One CTA owns one (batch, head).  Outer loop over key tiles j (128 keys), inner loop over
+// query tiles i (128 queries).  Per (j,i), five tcgen05 MMAs, all fed from the natural TMA
+// boxes [128 tokens x 64] of Q, K, V, dO (K-major or MN-major descriptors pick the
+// orientation - nothing is transposed in memory):
+//   S   = Q_i K_j^T          (queries on TMEM lanes)        [128 x 128]
+//   dP  = dO_i V_j^T                                        [128 x 128]
+//   threads: P = exp2(S*c - lse_i), dS = P * (dP - delta_i) * scale  -> bf16 in smem
+//   dV_j += P^T  dO_i        (A = P  as MN-major, B = dO_i as MN-major)   [128 x 64]
+//   dK_j += dS^T Q_i         (A = dS as MN-major, B = Q_i  as MN-major)   [128 x 64]
+//   dQ_i  = dS   K_j         (A = dS as K-major,  B = K_j  as MN-major)   [128 x 64]
+// dK_j/dV_j accumulate in TMEM across i.  dQ_i accumulates across the (<= 3) key tiles through
+// an fp32 workspace that the same thread re-reads (same CTA, same row: no atomics, L2 resident).
+#include "common.cuh"
+#include "host.h"
+
+namespace xclip {
+
+constexpr int kBwdThreads = 160;
+constexpr int kBT = 128;
+constexpr int kBDh = 64;
+constexpr int kBBox = kBT * kBDh * 2;  // 16 KiB
+
+struct AttnBwdParams {
+  int B, H, n;
+  float scale, scale_log2;
+  const uint8_t* mask;   // [B,n] or null
+  const float* lse;      // [B,H,n] base-2
+  const float* delta;    // [B,H,n] rowsum(dO * O)
+  bf16* dqkv;            // [B*n, ld] q | k | v gradients
+  long long ld;
+  float* dq_ws;          // fp32 [B*n, H*64] or null when n <= 128
+};
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]; one warp per (token, 4 heads at a time)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o,
+                  long long lddo, float* __restrict__ delta, int B, int n, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long tokens = (long long)B * n;
+  const int groups = (H + 3) / 4;  // 4 heads (256 elements) per warp pass, 8 lanes per head
+  for (long long w = warp; w < tokens * groups; w += nwarps) {
+    const long long tok = w / groups;
+    const int hg = (int)(w % groups);
+    const int h = hg * 4 + (lane >> 3);
+    float s = 0.f;
+    if (h < H) {
+      const int col = h * kBDh + (lane & 7) * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + tok * ldo + col);
+      const uint4 c = *reinterpret_cast<const uint4*>(d_o + tok * lddo + col);
+      const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16x2(aa[i]), y = unpack_bf16x2(cc[i]);
+        s += x.x * y.x + x.y * y.y;
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (h < H && (lane & 7) == 0) {
+      const long long b = tok / n, i = tok % n;
+      delta[(b * H + h) * n + i] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kBBox;
+  uint8_t* sQ = sV + kBBox;
+  uint8_t* sdO = sQ + kBBox;
+  uint8_t* sP = sdO + kBBox;        // 2 blocks of [128 x 64] bf16
+  uint8_t* sdS = sP + 2 * kBBox;    // 2 blocks
+  uint8_t* tail = sdS + 2 * kBBox;
+  uint64_t* kv_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* qdo_bar = kv_bar + 1;
+  uint64_t* s_bar = kv_bar + 2;
+  uint64_t* pds_bar = kv_bar + 3;
+  uint64_t* g_bar = kv_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 5);
+  uint8_t* sMask = tail + 64;  // [128] validity of the current key tile
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_bar, 1);
+    mbar_init(qdo_bar, 1);
+    mbar_init(s_bar, 1);
+    mbar_init(pds_bar, 4);
+    mbar_init(g_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+    }
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256,
+                 tdK = tmem_base + 320, tdQ = tmem_base + 384;
+
+  const int ntiles = (p.n + kBT - 1) / kBT;
+  const int inner = p.H * kBDh;
+  uint32_t kv_phase = 0, it_phase = 0;
+
+  for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
+    const int b = bh / p.H, h = bh % p.H;
+    for (int j = 0; j < ntiles; ++j) {
+      if (warp < 4) {
+        const int key = j * kBT + threadIdx.x;
+        sMask[threadIdx.x] =
+            (key < p.n) ? (p.mask ? p.mask[(long long)b * p.n + key] : (uint8_t)1) : (uint8_t)0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else if (lane == 0) {
+        mbar_arrive_expect_tx(kv_bar, 2 * kBBox);
+        tma_load_3d(sK, &tm_qkv, kv_bar, inner + h * kBDh, j * kBT, b);
+        tma_load_3d(sV, &tm_qkv, kv_bar, 2 * inner + h * kBDh, j * kBT, b);
+      }
+
+      for (int i = 0; i < ntiles; ++i) {
+        if (warp == 4) {
+          // ===================== control warp =====================
+          if (lane == 0) {
+            mbar_arrive_expect_tx(qdo_bar, 2 * kBBox);
+            tma_load_3d(sQ, &tm_qkv, qdo_bar, h * kBDh, i * kBT, b);
+            tma_load_3d(sdO, &tm_do, qdo_bar, h * kBDh, i * kBT, b);
+            if (i == 0) mbar_wait(kv_bar, kv_phase);
+            mbar_wait(qdo_bar, it_phase);
+            tcgen05_fence_after();
+            {
+              constexpr uint32_t idesc = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);
+              const uint64_t qd = make_smem_desc(smem_u32(sQ), 0, 1024);
+              const uint64_t kd = make_smem_desc(smem_u32(sK), 0, 1024);
+              const uint64_t dod = make_smem_desc(smem_u32(sdO), 0, 1024);
+              const uint64_t vd = make_smem_desc(smem_u32(sV), 0, 1024);
+#pragma unroll
+              for (int k = 0; k < kBDh / 16; ++k)
+                umma_bf16(tS, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc, k > 0);
+#pragma unroll
+              for (int k = 0; k < kBDh / 16; ++k)
+                umma_bf16(tdP, desc_advance(dod, k * 32), desc_advance(vd, k * 32), idesc, k > 0);
+            }
+            umma_commit(s_bar);
+
+            mbar_wait(pds_bar, it_phase);
+            tcgen05_fence_after();
+            {
+              constexpr uint32_t idesc_t = make_idesc_bf16(kBT, kBDh, kMajorMN, kMajorMN);
+              constexpr uint32_t idesc_q = make_idesc_bf16(kBT, kBDh, kMajorK, kMajorMN);
+#pragma unroll
+              for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 queries
+                const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
+                const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
+                const uint64_t dob = make_smem_desc(smem_u32(sdO) + k * 2048, 8192, 1024);
+                const uint64_t qb = make_smem_desc(smem_u32(sQ) + k * 2048, 8192, 1024);
+                umma_bf16(tdV, pT, dob, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(tdK, dsT, qb, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+              }
+#pragma unroll
+              for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 keys
+                const uint64_t dsk =
+                    make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
+                const uint64_t kb = make_smem_desc(smem_u32(sK) + k * 2048, 8192, 1024);
+                umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(g_bar);
+            mbar_wait(g_bar, it_phase);  // smem operands + S/dP TMEM reusable
+          }
+          __syncwarp();
+        } else {
+          // ===================== compute warps =====================
+          const int row = warp * 32 + lane;
+          const int q_idx = i * kBT + row;
+          const bool q_ok = q_idx < p.n;
+          const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+          float lse_i = 0.f, delta_i = 0.f;
+          if (q_ok) {
+            const long long s_idx = ((long long)b * p.H + h) * p.n + q_idx;
+            lse_i = p.lse[s_idx];
+            delta_i = p.delta[s_idx];
+          }
+          mbar_wait(s_bar, it_phase);
+          tcgen05_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < kBT; c0 += 32) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(tS + lane_off + c0, sv);
+            tmem_ld_32x32(tdP + lane_off + c0, dv);
+            tmem_ld_wait();
+            float pr[32], ds[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float pv = 0.f;
+              if (q_ok && sMask[c0 + e]) pv = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - lse_i);
+              pr[e] = pv;
+              ds[e] = pv * (__uint_as_float(dv[e]) - delta_i) * p.scale;
+            }
+            uint8_t* pblk = sP + (c0 >> 6) * kBBox;
+            uint8_t* dblk = sdS + (c0 >> 6) * kBBox;
+            const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 o;
+              o.x = pack_bf16x2(pr[cc * 8 + 0], pr[cc * 8 + 1]);
+              o.y = pack_bf16x2(pr[cc * 8 + 2], pr[cc * 8 + 3]);
+              o.z = pack_bf16x2(pr[cc * 8 + 4], pr[cc * 8 + 5]);
+              o.w = pack_bf16x2(pr[cc * 8 + 6], pr[cc * 8 + 7]);
+              *reinterpret_cast<uint4*>(pblk + swz128(row, chunk0 + cc)) = o;
+              o.x = pack_bf16x2(ds[cc * 8 + 0], ds[cc * 8 + 1]);
+              o.y = pack_bf16x2(ds[cc * 8 + 2], ds[cc * 8 + 3]);
+              o.z = pack_bf16x2(ds[cc * 8 + 4], ds[cc * 8 + 5]);
+              o.w = pack_bf16x2(ds[cc * 8 + 6], ds[cc * 8 + 7]);
+              *reinterpret_cast<uint4*>(dblk + swz128(row, chunk0 + cc)) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pds_bar);
+
+          // dQ_i partial for this key tile
+          mbar_wait(g_bar, it_phase);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tdQ + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (q_ok) {
+              const long long tok = (long long)b * p.n + q_idx;
+              float f[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+              float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + c * 32 : nullptr;
+              if (j > 0) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                  const float4 a = *reinterpret_cast<const float4*>(ws + e);
+                  f[e] += a.x; f[e + 1] += a.y; f[e + 2] += a.z; f[e + 3] += a.w;
+                }
+              }
+              if (j < ntiles - 1) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                  *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+              } else {
+                bf16* dst = p.dqkv + tok * p.ld + h * kBDh + c * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                  uint4 o;
+                  o.x = pack_bf16x2(f[e], f[e + 1]);
+                  o.y = pack_bf16x2(f[e + 2], f[e + 3]);
+                  o.z = pack_bf16x2(f[e + 4], f[e + 5]);
+                  o.w = pack_bf16x2(f[e + 6], f[e + 7]);
+                  *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+              }
+            }
+          }
+          tcgen05_fence_before();
+        }
+        it_phase ^= 1;
+      }  // i
+
+      // dK_j, dV_j complete (last g_bar was waited by everyone)
+      if (warp < 4) {
+        const int row = warp * 32 + lane;
+        const int key = j * kBT + row;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {   // 0: dK, 1: dV
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32((which == 0 ? tdK : tdV) + lane_off + c * 32, v);
+            tmem_ld_wait();
+            if (key < p.n) {
+              bf16* dst = p.dqkv + ((long long)b * p.n + key) * p.ld + (which + 1) * inner +
+                          h * kBDh + c * 32;
+#pragma unroll
+              for (int e = 0; e < 32; e += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+                o.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                o.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+                o.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+                *reinterpret_cast<uint4*>(dst + e) = o;
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+      }
+      kv_phase ^= 1;
+      __syncthreads();  // K/V smem, sMask and the dK/dV accumulators are free for the next tile
+    }  // j
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace xclip
+
+using namespace xclip;
+
+extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask,
+                              const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+                              const float* lse, float* delta, void* dqkv, int64_t ld_dqkv,
+                              float* dq_workspace, int B, int n, int heads, float scale,
+                              xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(qkv && o && d_o && lse && delta && dqkv, "attn_bwd: null pointer");
+  XCLIP_REQUIRE(B > 0 && heads > 0 && n > 0 && n <= 384, "attn_bwd: bad sizes B=%d n=%d heads=%d",
+                B, n, heads);
+  XCLIP_REQUIRE(n <= 128 || dq_workspace != nullptr,
+                "attn_bwd: n=%d > 128 needs the fp32 dq workspace [B*n, heads*64]", n);
+  XCLIP_REQUIRE(ld_qkv % 8 == 0 && ld_qkv >= 3 * heads * kBDh && ld_dqkv % 8 == 0 &&
+                    ld_dqkv >= 3 * heads * kBDh && ldo % 8 == 0 && lddo % 8 == 0 &&
+                    ldo >= heads * kBDh && lddo >= heads * kBDh,
+                "attn_bwd: bad leading dimensions");
+  XCLIP_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o) |
+                  reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(dqkv) |
+                  reinterpret_cast<uintptr_t>(dq_workspace)) & 15) == 0,
+                "attn_bwd: misaligned pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+  {
+    const long long warps = (long long)B * n * ((heads + 3) / 4);
+    long long blocks = (warps + 7) / 8;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    attn_delta_kernel<<<(int)blocks, 256, 0, s>>>((const bf16*)o, ldo, (const bf16*)d_o, lddo,
+                                                  delta, B, n, heads);
+    XCLIP_LAUNCH_CHECK("attn_delta_kernel");
+  }
+
+  AttnBwdParams p;
+  p.B = B; p.H = heads; p.n = n;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.mask = key_mask; p.lse = lse; p.delta = delta;
+  p.dqkv = reinterpret_cast<bf16*>(dqkv); p.ld = ld_dqkv; p.dq_ws = dq_workspace;
+
+  CUtensorMap tq, tdo;
+  rc = encode_3d_bf16(&tq, qkv, (uint64_t)(3 * heads * kBDh), (uint64_t)n, (uint64_t)B,
+                      (uint64_t)ld_qkv, (uint64_t)n * ld_qkv, kBDh, kBT);
+  if (rc) return rc;
+  rc = encode_3d_bf16(&tdo, d_o, (uint64_t)(heads * kBDh), (uint64_t)n, (uint64_t)B,
+                      (uint64_t)lddo, (uint64_t)n * lddo, kBDh, kBT);
+  if (rc) return rc;
+
+  const int smem = 8 * kBBox + 64 + 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem));
+    configured = true;
+  }
+  long long grid = num_sms();
+  if (grid > (long long)B * heads) grid = (long long)B * heads;
+  attn_bwd_kernel<<<(int)grid, kBwdThreads, smem, s>>>(tq, tdo, p);
+  XCLIP_LAUNCH_CHECK("attn_bwd_kernel");
+  return XCLIP_OK;
+}

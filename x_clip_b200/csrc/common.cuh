@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <float.h>
 #include <stdio.h>
 
 namespace xclip {

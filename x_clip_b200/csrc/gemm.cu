@@ -97,7 +97,7 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
   const long long total_tiles = tiles_mn * splits;
   int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
 
-  GemmParams p;
+  GemmParams p = {};
   p.M = M; p.N = N; p.K = K;
   p.c = c; p.ldc = ldc; p.c_is_f32 = c_dtype; p.atomic_add = accumulate ? 1 : 0;
   p.split_k = splits; p.alpha = alpha; p.bias = bias;

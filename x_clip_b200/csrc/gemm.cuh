@@ -35,7 +35,20 @@ struct GemmParams {
   const bf16* residual;  // bf16 [*, N] or null
   long long ldr;
   int res_row_mod;     // residual row = row % res_row_mod when > 0 (positional tables)
+  // ---- InfoNCE / DCL epilogues (EPI_NCE_FWD, EPI_NCE_BWD); logits s = alpha * acc, alpha = exp(temperature)
+  int diag_offset;       // positive of local row r sits in column r + diag_offset
+  int dcl;               // decoupled contrastive learning: drop the positive from the denominators
+  float* nce_part;       // FWD: [num_n_blocks, M] partial sums of exp(s - alpha)
+  float* nce_pos;        // FWD: [M] positive logits
+  const float* lse_row;  // BWD: [M]  log-denominator of each row (this direction)
+  const float* lse_col;  // BWD: [N]  log-denominator of each column (other direction)
+  float w_row, w_col, w_diag;
+  float* dtemp;          // BWD: scalar accumulator of sum(g * s) or null
 };
+
+constexpr int EPI_STORE = 0;    // C = alpha*acc (+bias) (+residual)
+constexpr int EPI_NCE_FWD = 1;  // row partial sums of exp(s - alpha) and the positives
+constexpr int EPI_NCE_BWD = 2;  // C = g = w_row*exp(s-lse_row) + w_col*exp(s-lse_col) - w_diag*[diag]
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
@@ -51,7 +64,7 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + align slack
 };
 
-template <int BLOCK_N, int A_MAJOR, int B_MAJOR>
+template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -204,70 +217,141 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
         res_row = p.residual + rr * p.ldr;
       }
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (row_ok && col0 < p.N) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-          if (p.bias != nullptr && split == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (col0 + i < p.N) {
-                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
-                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-              }
-            }
-          }
-          if (res_row != nullptr && split == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {
-                const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
-                float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
-                float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
-                f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
-                f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
-              }
-            }
-          }
-          if (p.c_is_f32) {
-            float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
-            if (p.atomic_add) {
-#pragma unroll
+      if constexpr (EPI == EPI_STORE) {
+  #pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          if (row_ok && col0 < p.N) {
+            float f[32];
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+            if (p.bias != nullptr && split == 0) {
+  #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 if (col0 + i < p.N) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i),
-                               "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
-                               : "memory");
+                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+                  f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                }
+              }
+            }
+            if (res_row != nullptr && split == 0) {
+  #pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {
+                  const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
+                  float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
+                  float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+                  f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
+                  f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
+                }
+              }
+            }
+            if (p.c_is_f32) {
+              float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+              if (p.atomic_add) {
+  #pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (col0 + i < p.N) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i),
+                                 "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
+                                 : "memory");
+                  }
+                }
+              } else {
+  #pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (col0 + i < p.N)
+                    *reinterpret_cast<float4*>(crow + i) =
+                        make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
                 }
               }
             } else {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                if (col0 + i < p.N)
-                  *reinterpret_cast<float4*>(crow + i) =
-                      make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+  #pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {
+                  uint4 o;
+                  o.x = pack_bf16x2(f[i], f[i + 1]);
+                  o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+                  o.z = pack_bf16x2(f[i + 4], f[i + 5]);
+                  o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(crow + i) = o;
+                }
               }
             }
-          } else {
+          }
+        }
+      } else if constexpr (EPI == EPI_NCE_FWD) {
+        // s = alpha*acc with |s| <= alpha (unit-norm latents): exp(s - alpha) cannot overflow.
+        const float a2 = p.alpha * 1.4426950408889634f;
+        const int diag_col = row + p.diag_offset;
+        float rsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = col0 + i;
+            const float acc_v = __uint_as_float(v[i]);
+            const bool is_diag = (col == diag_col);
+            if (is_diag && row_ok) p.nce_pos[row] = acc_v * p.alpha;
+            if (col < p.N && !(p.dcl && is_diag)) rsum += exp2f(acc_v * a2 - a2);
+          }
+        }
+        if (row_ok) p.nce_part[(long long)n_blk * p.M + row] = rsum;
+      } else {
+        const float a2 = p.alpha * 1.4426950408889634f;
+        const int diag_col = row + p.diag_offset;
+        const float lr2 = (row_ok && p.lse_row) ? p.lse_row[row] * 1.4426950408889634f : 0.f;
+        float tsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          if (row_ok && col0 < p.N) {
+            float gq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              const float acc_v = __uint_as_float(v[i]);
+              const bool is_diag = (col == diag_col);
+              float gv = 0.f;
+              if (col < p.N) {
+                if (!(p.dcl && is_diag)) {
+                  if (p.w_row != 0.f) gv += p.w_row * exp2f(acc_v * a2 - lr2);
+                  if (p.w_col != 0.f)
+                    gv += p.w_col * exp2f(acc_v * a2 - p.lse_col[col] * 1.4426950408889634f);
+                }
+                if (is_diag) gv -= p.w_diag;
+                tsum += gv * acc_v * p.alpha;
+              }
+              gq[i] = gv;
+            }
             bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               if (col0 + i < p.N) {
                 uint4 o;
-                o.x = pack_bf16x2(f[i], f[i + 1]);
-                o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                o.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                o.x = pack_bf16x2(gq[i], gq[i + 1]);
+                o.y = pack_bf16x2(gq[i + 2], gq[i + 3]);
+                o.z = pack_bf16x2(gq[i + 4], gq[i + 5]);
+                o.w = pack_bf16x2(gq[i + 6], gq[i + 7]);
                 *reinterpret_cast<uint4*>(crow + i) = o;
               }
             }
           }
+        }
+        if (p.dtemp != nullptr) {
+          tsum = warp_sum(tsum);
+          if (lane == 0) atomicAdd(p.dtemp, tsum);
         }
       }
       tcgen05_fence_before();

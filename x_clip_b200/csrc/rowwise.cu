@@ -1,0 +1,574 @@
+// Row-wise HBM-bound kernels of the transformer block and the latent head:
+//   gain-only LayerNorm fwd/bwd   (reference x_clip/x_clip.py:112-121; used at :126,:210,:193,:271-272)
+//   GEGLU + LayerNorm fwd/bwd     (reference :180-183 + :193 inside FeedForward :185-199)
+//   l2-normalise fwd/bwd          (reference :54-55, called at :715,:724)
+//   fp32 -> bf16 cast             (weights are kept fp32 by the module; MMA operands are bf16)
+//
+// One warp owns one row; a lane owns 16-byte vectors (8 bf16) strided by 32 lanes so every
+// warp-wide access is a fully coalesced 512-byte segment.  Row statistics are reduced with
+// warp shuffles in fp32.  Column reductions (gain gradients) are accumulated per lane in
+// registers over the rows a warp visits, combined across the block in shared memory and
+// added to the fp32 output with one atomic per column per block.
+#include "common.cuh"
+#include "host.h"
+
+namespace xclip {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+         d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+__device__ __forceinline__ void storef8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+__device__ __forceinline__ float bf16_round(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+// Adds the per-lane column partials of all warps of the block and issues one atomicAdd per column.
+template <int NV>
+__device__ __forceinline__ void flush_column_partials(float (&acc)[NV][8], float* dst,
+                                                      float* smem /* [NV*256] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < NV * 256; i += kRowThreads) smem[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&smem[(j * 32 + lane) * 8 + e], acc[j][e]);
+  (void)warp;
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV * 256; i += kRowThreads) atomicAdd(dst + i, smem[i]);
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm forward:  out = LN(x) * g (+ res);  optionally out2 = LN(bf16(out)) * g2
+// stats = (mean, rstd) per row of the FIRST norm, stats2 of the second.
+// ---------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ g,
+              const bf16* __restrict__ res, long long ldres, bf16* __restrict__ out,
+              long long ldo, float* __restrict__ stats, const float* __restrict__ g2,
+              bf16* __restrict__ out2, long long ldo2, float* __restrict__ stats2, int rows,
+              float eps) {
+  constexpr int D = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * kRowWarps;
+  for (int row = warp_global; row < rows; row += warp_stride) {
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      load8(x + row * ldx + (j * 32 + lane) * 8, v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    }
+    const float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float c = v[j][e] - mean; q += c * c; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+    if (lane == 0 && stats != nullptr) {
+      stats[2 * (long long)row] = mean;
+      stats[2 * (long long)row + 1] = rstd;
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+      float gg[8];
+      loadf8(g + col, gg);
+      float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (res != nullptr) load8(res + row * ldres + col, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] = (v[j][e] - mean) * rstd * gg[e] + r[e];
+      store8(out + row * ldo + col, v[j]);
+      if (g2 != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[j][e] = bf16_round(v[j][e]); s2 += v[j][e]; }
+      }
+    }
+    if (g2 != nullptr) {
+      const float mean2 = warp_sum(s2) * (1.f / D);
+      float q2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float c = v[j][e] - mean2; q2 += c * c; }
+      const float rstd2 = rsqrtf(warp_sum(q2) * (1.f / D) + eps);
+      if (lane == 0 && stats2 != nullptr) {
+        stats2[2 * (long long)row] = mean2;
+        stats2[2 * (long long)row + 1] = rstd2;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int col = (j * 32 + lane) * 8;
+        float gg[8];
+        loadf8(g2 + col, gg);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean2) * rstd2 * gg[e];
+        store8(out2 + row * ldo2 + col, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm backward: dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ add)
+//                     dg += sum_rows dy * xhat
+// ---------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x,
+              long long ldx, const float* __restrict__ stats, const float* __restrict__ g,
+              const bf16* __restrict__ add, long long ldadd, bf16* __restrict__ dx,
+              long long lddx, float* __restrict__ dg, int rows) {
+  constexpr int D = NV * 256;
+  __shared__ float red[NV * 256];
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * kRowWarps;
+  float dgacc[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dgacc[j][e] = 0.f;
+  float gg[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) loadf8(g + (j * 32 + lane) * 8, gg[j]);
+
+  for (int row = warp_global; row < rows; row += warp_stride) {
+    const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
+    float xh[NV][8], gd[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+      float d8[8];
+      load8(x + row * ldx + col, xh[j]);
+      load8(dy + row * lddy + col, d8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[j][e] = (xh[j][e] - mean) * rstd;
+        dgacc[j][e] += d8[e] * xh[j][e];
+        gd[j][e] = d8[e] * gg[j][e];
+        s1 += gd[j][e];
+        s2 += gd[j][e] * xh[j][e];
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / D);
+    s2 = warp_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+      float a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (add != nullptr) load8(add + row * ldadd + col, a8);
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (gd[j][e] - s1 - xh[j][e] * s2) + a8[e];
+      store8(dx + row * lddx + col, o);
+    }
+  }
+  if (dg != nullptr) flush_column_partials<NV>(dgacc, dg, red);
+}
+
+// ---------------------------------------------------------------------------
+// GEGLU + LayerNorm.  u = [val | gate] (each DH wide).  v = val * gelu_erf(gate)
+//   fwd: h = LN(v) * g ; stats = (mean, rstd) of v
+//   bwd: dv = LN-bwd(dh);  dval = dv * gelu(gate);  dgate = dv * val * gelu'(gate)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) +
+         x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// The hidden width (4*dim) is 1024..4096, too wide for one warp's registers, so these two
+// kernels give one ROW to a 128-thread block: thread t owns 16-byte vectors t, t+128, ...
+constexpr int kWideThreads = 128;
+
+__device__ __forceinline__ float2 block_sum2(float a, float b, float* scratch /* [8] */) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // scratch reuse across rows
+  if (lane == 0) { scratch[warp] = a; scratch[4 + warp] = b; }
+  __syncthreads();
+  return make_float2(scratch[0] + scratch[1] + scratch[2] + scratch[3],
+                     scratch[4] + scratch[5] + scratch[6] + scratch[7]);
+}
+
+template <int NV>  // NV = DH / 1024
+__global__ void __launch_bounds__(kWideThreads)
+geglu_ln_fwd_kernel(const bf16* __restrict__ u, long long ldu, const float* __restrict__ g,
+                    bf16* __restrict__ h, long long ldh, float* __restrict__ stats, int rows,
+                    float eps) {
+  constexpr int DH = NV * 1024;
+  __shared__ float scratch[8];
+  const int t = threadIdx.x;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * kWideThreads + t) * 8;
+      float gt[8];
+      load8(u + row * ldu + col, v[j]);
+      load8(u + row * ldu + DH + col, gt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[j][e] *= gelu_erf(gt[e]); s += v[j][e]; }
+    }
+    const float mean = block_sum2(s, 0.f, scratch).x * (1.f / DH);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float c = v[j][e] - mean; q += c * c; }
+    const float rstd = rsqrtf(block_sum2(q, 0.f, scratch).x * (1.f / DH) + eps);
+    if (t == 0) {
+      stats[2 * (long long)row] = mean;
+      stats[2 * (long long)row + 1] = rstd;
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * kWideThreads + t) * 8;
+      float gg[8], o[8];
+      loadf8(g + col, gg);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e];
+      store8(h + row * ldh + col, o);
+    }
+  }
+}
+
+template <int NV>  // NV = DH / 1024
+__global__ void __launch_bounds__(kWideThreads)
+geglu_ln_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __restrict__ u,
+                    long long ldu, const float* __restrict__ stats, const float* __restrict__ g,
+                    bf16* __restrict__ du, long long lddu, float* __restrict__ dg, int rows) {
+  constexpr int DH = NV * 1024;
+  __shared__ float scratch[8];
+  const int t = threadIdx.x;
+  float dgacc[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dgacc[j][e] = 0.f;
+
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
+    float va[NV][8], gt[NV][8], gd[NV][8];  // value, gate, gain*dh
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * kWideThreads + t) * 8;
+      float gg[8];
+      load8(u + row * ldu + col, va[j]);
+      load8(u + row * ldu + DH + col, gt[j]);
+      load8(dh + row * lddh + col, gd[j]);
+      loadf8(g + col, gg);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float vh = (va[j][e] * gelu_erf(gt[j][e]) - mean) * rstd;
+        dgacc[j][e] += gd[j][e] * vh;
+        gd[j][e] *= gg[e];
+        s1 += gd[j][e];
+        s2 += gd[j][e] * vh;
+      }
+    }
+    const float2 ss = block_sum2(s1, s2, scratch);
+    s1 = ss.x * (1.f / DH);
+    s2 = ss.y * (1.f / DH);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * kWideThreads + t) * 8;
+      float o_val[8], o_gate[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float ge = gelu_erf(gt[j][e]);
+        const float vh = (va[j][e] * ge - mean) * rstd;
+        const float dv = rstd * (gd[j][e] - s1 - vh * s2);
+        o_val[e] = dv * ge;
+        o_gate[e] = dv * va[j][e] * gelu_erf_grad(gt[j][e]);
+      }
+      store8(du + row * lddu + col, o_val);
+      store8(du + row * lddu + DH + col, o_gate);
+    }
+  }
+  if (dg != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(dg + (j * kWideThreads + t) * 8 + e, dgacc[j][e]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// l2-normalise rows of an fp32 matrix: z = p / max(||p||, 1e-12)
+//   fwd writes z (fp32), z16 (bf16, operand of the logits MMA) and inv = 1/max(||p||,eps)
+//   bwd: dp = inv * (dz - z * <z, dz>)   (bf16, operand of the projection dgrad/wgrad)
+// ---------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+l2norm_fwd_kernel(const float* __restrict__ p, long long ldp, float* __restrict__ z,
+                  bf16* __restrict__ z16, float* __restrict__ inv, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * kRowWarps;
+  constexpr int D = NV * 256;
+  for (int row = warp_global; row < rows; row += warp_stride) {
+    float v[NV][8];
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      loadf8(p + row * ldp + (j * 32 + lane) * 8, v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q += v[j][e] * v[j][e];
+    }
+    const float r = 1.f / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
+    if (lane == 0) inv[row] = r;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] *= r;
+      storef8(z + (long long)row * D + col, v[j]);
+      store8(z16 + (long long)row * D + col, v[j]);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+l2norm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ z,
+                  const float* __restrict__ inv, bf16* __restrict__ dp, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * kRowWarps;
+  constexpr int D = NV * 256;
+  for (int row = warp_global; row < rows; row += warp_stride) {
+    float a[NV][8], b[NV][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+      loadf8(dz + (long long)row * D + col, a[j]);
+      loadf8(z + (long long)row * D + col, b[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot += a[j][e] * b[j][e];
+    }
+    dot = warp_sum(dot);
+    const float r = inv[row];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = r * (a[j][e] - b[j][e] * dot);
+      store8(dp + (long long)row * D + col, o);
+    }
+  }
+}
+
+// flat fp32 -> bf16
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n8 = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    loadf8(src + i * 8, f);
+    store8(dst + i * 8, f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7))
+    dst[n8 * 8 + threadIdx.x] = __float2bfloat16_rn(src[n8 * 8 + threadIdx.x]);
+}
+
+static int row_grid(int rows) {
+  const int blocks = (rows + kRowWarps - 1) / kRowWarps;
+  const int cap = num_sms() * 8;
+  return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+}
+
+static int wide_grid(int rows, int per_sm) {
+  const int cap = num_sms() * per_sm;
+  return rows < cap ? rows : cap;
+}
+
+}  // namespace xclip
+
+using namespace xclip;
+
+#define LAUNCH_NV(KERNEL, NVAL, GRID, STREAM, ...) \
+  case NVAL: KERNEL<NVAL><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;
+
+#define LAUNCH_WIDE(KERNEL, NVAL, GRID, STREAM, ...) \
+  case NVAL: KERNEL<NVAL><<<GRID, kWideThreads, 0, STREAM>>>(__VA_ARGS__); break;
+
+// feed-forward hidden widths 1024*{1,2,3,4} (= 4*dim for dim 256..1024): one block per row
+#define DISPATCH_WIDE(KERNEL, D, GRID, STREAM, ...)                                       \
+  switch ((D) / 1024) {                                                                   \
+    LAUNCH_WIDE(KERNEL, 1, GRID, STREAM, __VA_ARGS__)                                     \
+    LAUNCH_WIDE(KERNEL, 2, GRID, STREAM, __VA_ARGS__)                                     \
+    LAUNCH_WIDE(KERNEL, 3, GRID, STREAM, __VA_ARGS__)                                     \
+    LAUNCH_WIDE(KERNEL, 4, GRID, STREAM, __VA_ARGS__)                                     \
+    default:                                                                              \
+      return fail(XCLIP_ERR_INVALID, "hidden width %d unsupported (1024*{1,2,3,4})", (D)); \
+  }
+
+#define DISPATCH_NARROW(KERNEL, D, GRID, STREAM, ...)                                     \
+  switch ((D) / 256) {                                                                    \
+    LAUNCH_NV(KERNEL, 1, GRID, STREAM, __VA_ARGS__)                                       \
+    LAUNCH_NV(KERNEL, 2, GRID, STREAM, __VA_ARGS__)                                       \
+    LAUNCH_NV(KERNEL, 3, GRID, STREAM, __VA_ARGS__)                                       \
+    LAUNCH_NV(KERNEL, 4, GRID, STREAM, __VA_ARGS__)                                       \
+    default:                                                                              \
+      return fail(XCLIP_ERR_INVALID, "row width %d unsupported (256*{1,2,3,4})", (D));    \
+  }
+
+#define ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int xclip_layernorm_fwd(const void* x, int64_t ldx, const float* g, const void* res,
+                                   int64_t ldres, void* out, int64_t ldo, float* stats,
+                                   const float* g2, void* out2, int64_t ldo2, float* stats2,
+                                   int rows, int d, float eps, xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(x && g && out, "layernorm_fwd: null pointer");
+  XCLIP_REQUIRE(rows > 0, "layernorm_fwd: rows=%d", rows);
+  XCLIP_REQUIRE(d % 256 == 0, "layernorm_fwd: d=%d must be a multiple of 256", d);
+  XCLIP_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldres % 8 == 0) && (!g2 || ldo2 % 8 == 0),
+                "layernorm_fwd: leading dims must be multiples of 8");
+  XCLIP_REQUIRE(ALIGNED16(x) && ALIGNED16(out) && ALIGNED16(g) && (!res || ALIGNED16(res)) &&
+                    (!g2 || (ALIGNED16(g2) && out2 && ALIGNED16(out2))),
+                "layernorm_fwd: pointers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NARROW(ln_fwd_kernel, d, row_grid(rows), s, (const bf16*)x, ldx, g, (const bf16*)res,
+                  ldres, (bf16*)out, ldo, stats, g2, (bf16*)out2, ldo2, stats2, rows, eps)
+  XCLIP_LAUNCH_CHECK("ln_fwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                                   const float* stats, const float* g, const void* add,
+                                   int64_t ldadd, void* dx, int64_t lddx, float* dg, int rows,
+                                   int d, xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(dy && x && stats && g && dx, "layernorm_bwd: null pointer");
+  XCLIP_REQUIRE(rows > 0 && d % 256 == 0, "layernorm_bwd: rows=%d d=%d", rows, d);
+  XCLIP_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (!add || ldadd % 8 == 0),
+                "layernorm_bwd: leading dims must be multiples of 8");
+  XCLIP_REQUIRE(ALIGNED16(dy) && ALIGNED16(x) && ALIGNED16(dx) && ALIGNED16(g) &&
+                    (!add || ALIGNED16(add)),
+                "layernorm_bwd: pointers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = row_grid(rows) < num_sms() * 2 ? row_grid(rows) : num_sms() * 2;
+  DISPATCH_NARROW(ln_bwd_kernel, d, grid, s, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, g,
+                  (const bf16*)add, ldadd, (bf16*)dx, lddx, dg, rows)
+  XCLIP_LAUNCH_CHECK("ln_bwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_geglu_ln_fwd(const void* u, int64_t ldu, const float* g, void* h, int64_t ldh,
+                                  float* stats, int rows, int dh, float eps,
+                                  xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(u && g && h && stats, "geglu_ln_fwd: null pointer");
+  XCLIP_REQUIRE(rows > 0 && dh % 1024 == 0, "geglu_ln_fwd: rows=%d dh=%d (dh %% 1024)", rows, dh);
+  XCLIP_REQUIRE(ldu % 8 == 0 && ldh % 8 == 0 && ldu >= 2 * dh, "geglu_ln_fwd: bad leading dims");
+  XCLIP_REQUIRE(ALIGNED16(u) && ALIGNED16(h) && ALIGNED16(g), "geglu_ln_fwd: misaligned pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_WIDE(geglu_ln_fwd_kernel, dh, wide_grid(rows, 12), s, (const bf16*)u, ldu, g, (bf16*)h, ldh,
+                stats, rows, eps)
+  XCLIP_LAUNCH_CHECK("geglu_ln_fwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_geglu_ln_bwd(const void* dh_, int64_t lddh, const void* u, int64_t ldu,
+                                  const float* stats, const float* g, void* du, int64_t lddu,
+                                  float* dg, int rows, int dh, xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(dh_ && u && stats && g && du, "geglu_ln_bwd: null pointer");
+  XCLIP_REQUIRE(rows > 0 && dh % 1024 == 0, "geglu_ln_bwd: rows=%d dh=%d (dh %% 1024)", rows, dh);
+  XCLIP_REQUIRE(lddh % 8 == 0 && ldu % 8 == 0 && lddu % 8 == 0 && ldu >= 2 * dh && lddu >= 2 * dh,
+                "geglu_ln_bwd: bad leading dims");
+  XCLIP_REQUIRE(ALIGNED16(dh_) && ALIGNED16(u) && ALIGNED16(du) && ALIGNED16(g),
+                "geglu_ln_bwd: misaligned pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_WIDE(geglu_ln_bwd_kernel, dh, wide_grid(rows, 4), s, (const bf16*)dh_, lddh, (const bf16*)u, ldu,
+                stats, g, (bf16*)du, lddu, dg, rows)
+  XCLIP_LAUNCH_CHECK("geglu_ln_bwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_l2norm_fwd(const float* p, int64_t ldp, float* z, void* z16, float* inv,
+                                int rows, int d, xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(p && z && z16 && inv, "l2norm_fwd: null pointer");
+  XCLIP_REQUIRE(rows > 0 && d % 256 == 0, "l2norm_fwd: rows=%d d=%d", rows, d);
+  XCLIP_REQUIRE(ldp % 4 == 0 && ALIGNED16(p) && ALIGNED16(z) && ALIGNED16(z16),
+                "l2norm_fwd: misaligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NARROW(l2norm_fwd_kernel, d, row_grid(rows), s, p, ldp, z, (bf16*)z16, inv, rows)
+  XCLIP_LAUNCH_CHECK("l2norm_fwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_l2norm_bwd(const float* dz, const float* z, const float* inv, void* dp,
+                                int rows, int d, xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(dz && z && inv && dp, "l2norm_bwd: null pointer");
+  XCLIP_REQUIRE(rows > 0 && d % 256 == 0, "l2norm_bwd: rows=%d d=%d", rows, d);
+  XCLIP_REQUIRE(ALIGNED16(dz) && ALIGNED16(z) && ALIGNED16(dp), "l2norm_bwd: misaligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_NARROW(l2norm_bwd_kernel, d, row_grid(rows), s, dz, z, inv, (bf16*)dp, rows)
+  XCLIP_LAUNCH_CHECK("l2norm_bwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_cast_f32_bf16(const float* src, void* dst, int64_t n, xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(src && dst && n > 0, "cast: bad arguments");
+  XCLIP_REQUIRE(ALIGNED16(src) && ALIGNED16(dst), "cast: misaligned");
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, (bf16*)dst, n);
+  XCLIP_LAUNCH_CHECK("cast_f32_bf16_kernel");
+  return XCLIP_OK;
+}

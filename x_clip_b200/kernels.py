@@ -75,3 +75,139 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
               float(alpha), _ptr(bias), _ptr(residual), ldr, int(res_row_mod),
               1 if accumulate else 0, _stream())
     return out
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy of a contiguous tensor (weights before they are MMA operands)."""
+    _need(src, F32, "src")
+    src = src.contiguous()
+    dst = torch.empty(src.shape, device=src.device, dtype=BF16)
+    if src.numel():
+        _lib.call("xclip_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    return dst
+
+
+def layernorm_fwd(x, g, *, res=None, g2=None, eps=1e-5, want_stats=True):
+    """out = LN(x)*g (+res); optionally out2 = LN(out)*g2.  Returns (out, stats, out2, stats2)."""
+    _need(x, BF16, "x"); _rows2d(x, "x"); _need(g, F32, "g")
+    rows, d = x.shape
+    out = torch.empty((rows, d), device=x.device, dtype=BF16)
+    stats = torch.empty((rows, 2), device=x.device, dtype=F32) if want_stats else None
+    out2 = stats2 = None
+    if g2 is not None:
+        _need(g2, F32, "g2")
+        out2 = torch.empty((rows, d), device=x.device, dtype=BF16)
+        stats2 = torch.empty((rows, 2), device=x.device, dtype=F32)
+    if res is not None:
+        _need(res, BF16, "res"); _rows2d(res, "res")
+    _lib.call("xclip_layernorm_fwd", x.data_ptr(), x.stride(0), g.data_ptr(), _ptr(res),
+              res.stride(0) if res is not None else 0, out.data_ptr(), out.stride(0), _ptr(stats),
+              _ptr(g2), _ptr(out2), out2.stride(0) if out2 is not None else 0, _ptr(stats2),
+              rows, d, float(eps), _stream())
+    return out, stats, out2, stats2
+
+
+def layernorm_bwd(dy, x, stats, g, *, add=None, dg=None):
+    """dx = dLN(dy) (+add); dg (fp32 [d]) is accumulated into when given."""
+    _need(dy, BF16, "dy"); _need(x, BF16, "x"); _rows2d(dy, "dy"); _rows2d(x, "x")
+    rows, d = x.shape
+    dx = torch.empty((rows, d), device=x.device, dtype=BF16)
+    if add is not None:
+        _need(add, BF16, "add"); _rows2d(add, "add")
+    _lib.call("xclip_layernorm_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
+              stats.data_ptr(), g.data_ptr(), _ptr(add), add.stride(0) if add is not None else 0,
+              dx.data_ptr(), dx.stride(0), _ptr(dg), rows, d, _stream())
+    return dx
+
+
+def geglu_ln_fwd(u, g, *, eps=1e-5):
+    _need(u, BF16, "u"); _rows2d(u, "u"); _need(g, F32, "g")
+    rows, two_dh = u.shape
+    dh = two_dh // 2
+    h = torch.empty((rows, dh), device=u.device, dtype=BF16)
+    stats = torch.empty((rows, 2), device=u.device, dtype=F32)
+    _lib.call("xclip_geglu_ln_fwd", u.data_ptr(), u.stride(0), g.data_ptr(), h.data_ptr(),
+              h.stride(0), stats.data_ptr(), rows, dh, float(eps), _stream())
+    return h, stats
+
+
+def geglu_ln_bwd(dh_grad, u, stats, g, *, dg=None):
+    _need(dh_grad, BF16, "dh"); _rows2d(dh_grad, "dh"); _need(u, BF16, "u")
+    rows, two_dh = u.shape
+    du = torch.empty((rows, two_dh), device=u.device, dtype=BF16)
+    _lib.call("xclip_geglu_ln_bwd", dh_grad.data_ptr(), dh_grad.stride(0), u.data_ptr(),
+              u.stride(0), stats.data_ptr(), g.data_ptr(), du.data_ptr(), du.stride(0), _ptr(dg),
+              rows, two_dh // 2, _stream())
+    return du
+
+
+def l2norm_fwd(p):
+    _need(p, F32, "p"); _rows2d(p, "p")
+    rows, d = p.shape
+    z = torch.empty((rows, d), device=p.device, dtype=F32)
+    z16 = torch.empty((rows, d), device=p.device, dtype=BF16)
+    inv = torch.empty((rows,), device=p.device, dtype=F32)
+    _lib.call("xclip_l2norm_fwd", p.data_ptr(), p.stride(0), z.data_ptr(), z16.data_ptr(),
+              inv.data_ptr(), rows, d, _stream())
+    return z, z16, inv
+
+
+def l2norm_bwd(dz, z, inv):
+    _need(dz, F32, "dz"); _need(z, F32, "z")
+    dz = dz.contiguous()
+    rows, d = z.shape
+    dp = torch.empty((rows, d), device=z.device, dtype=BF16)
+    _lib.call("xclip_l2norm_bwd", dz.data_ptr(), z.data_ptr(), inv.data_ptr(), dp.data_ptr(),
+              rows, d, _stream())
+    return dp
+
+
+def attn_fwd(qkv, key_mask, B, n, heads, scale):
+    """qkv bf16 [B*n, 3*heads*64] -> (o bf16 [B*n, heads*64], lse f32 [B, heads, n])."""
+    _need(qkv, BF16, "qkv"); _rows2d(qkv, "qkv")
+    o = torch.empty((B * n, heads * 64), device=qkv.device, dtype=BF16)
+    lse = torch.empty((B, heads, n), device=qkv.device, dtype=F32)
+    if key_mask is not None:
+        if key_mask.dtype != torch.bool or tuple(key_mask.shape) != (B, n) or not key_mask.is_contiguous():
+            raise _lib.XClipB200Error("attn_fwd: key_mask must be a contiguous bool [B, n]")
+    _lib.call("xclip_attn_fwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
+              o.stride(0), lse.data_ptr(), B, n, heads, float(scale), _stream())
+    return o, lse
+
+
+def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale):
+    _need(d_o, BF16, "d_o"); _rows2d(d_o, "d_o")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, heads, n), device=qkv.device, dtype=F32)
+    ws = torch.empty((B * n, heads * 64), device=qkv.device, dtype=F32) if n > 128 else None
+    _lib.call("xclip_attn_bwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
+              o.stride(0), d_o.data_ptr(), d_o.stride(0), lse.data_ptr(), delta.data_ptr(),
+              dqkv.data_ptr(), dqkv.stride(0), _ptr(ws), B, n, heads, float(scale), _stream())
+    return dqkv
+
+
+def nce_fwd(a, b, temp_exp, diag_offset, dcl, loss_accum=None, loss_scale=0.0):
+    """Row-block InfoNCE forward: returns (lse [R], pos [R]) for rows a against all columns b."""
+    _need(a, BF16, "a"); _need(b, BF16, "b")
+    R, D = a.shape
+    C = b.shape[0]
+    nblk = _lib.load().xclip_nce_num_col_blocks(C)
+    part = torch.empty((nblk, R), device=a.device, dtype=F32)
+    pos = torch.empty((R,), device=a.device, dtype=F32)
+    lse = torch.empty((R,), device=a.device, dtype=F32)
+    _lib.call("xclip_nce_fwd", a.data_ptr(), b.data_ptr(), R, C, D, float(temp_exp),
+              int(diag_offset), 1 if dcl else 0, part.data_ptr(), pos.data_ptr(), lse.data_ptr(),
+              _ptr(loss_accum), float(loss_scale), _stream())
+    return lse, pos
+
+
+def nce_bwd(a, b, temp_exp, diag_offset, dcl, lse_row, lse_col, w_row, w_col, w_diag, dtemp=None):
+    """g bf16 [R, roundup8(C)] (columns >= C are zero); see xclip_nce_bwd."""
+    R, D = a.shape
+    C = b.shape[0]
+    ldg = (C + 7) // 8 * 8
+    g = torch.empty((R, ldg), device=a.device, dtype=BF16)
+    _lib.call("xclip_nce_bwd", a.data_ptr(), b.data_ptr(), R, C, D, float(temp_exp),
+              int(diag_offset), 1 if dcl else 0, _ptr(lse_row), _ptr(lse_col), float(w_row),
+              float(w_col), float(w_diag), g.data_ptr(), ldg, _ptr(dtemp), _stream())
+    return g
