@@ -88,9 +88,12 @@ int xclip_geglu_ln_bwd(const void* dh_grad, int64_t lddh, const void* u, int64_t
                        const float* stats, const float* g, void* du, int64_t lddu, float* dg,
                        int rows, int dh, xclip_stream_t stream);
 /* l2norm = F.normalize(dim=-1, eps=1e-12) (x_clip/x_clip.py:54-55, used at :715,:724).
- * p f32 [rows,d] -> z f32, z16 bf16 (MMA operand of the logits), inv = 1/max(|p|,eps). */
-int xclip_l2norm_fwd(const float* p, int64_t ldp, float* z, void* z16, float* inv, int rows,
-                     int d, xclip_stream_t stream);
+ * p f32 [rows,d] -> z f32 [rows,d], inv = 1/max(|p|,eps), and the split-bf16 operands of the
+ * logits contraction: zrow = [hi|lo|hi], zcol = [hi|hi|lo], bf16 [rows,3d], hi = bf16(z),
+ * lo = bf16(z - hi).  zrow . zcol^T = hi.hi + lo.hi + hi.lo matches the fp32 dot product to
+ * ~2^-17, so the logits keep fp32-level accuracy while running on the bf16 tensor cores. */
+int xclip_l2norm_fwd(const float* p, int64_t ldp, float* z, void* zrow, void* zcol, float* inv,
+                     int rows, int d, xclip_stream_t stream);
 /* dp (bf16) = inv * (dz - z <z,dz>) */
 int xclip_l2norm_bwd(const float* dz, const float* z, const float* inv, void* dp, int rows, int d,
                      xclip_stream_t stream);
@@ -112,25 +115,27 @@ int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, con
 
 /* ---- similarity + InfoNCE / DCL (tcgen05, logits never materialised in forward) ----------
  * Replaces x_clip/x_clip.py:813-847 for one direction of the loss:
- *   s[r,c] = temp_exp * <a_r, b_c>,  a bf16 [R,D] = LOCAL unit-norm latents of one modality,
+ *   s[r,c] = *temp_exp * <a_r, b_c> (temp_exp: DEVICE scalar exp(temperature), so the host
+ *   never synchronises on the parameter),  a bf16 [R,D] = LOCAL unit-norm latents of one modality,
  *   b bf16 [C,D] = ALL latents of the other modality; the positive of row r is column
  *   r + diag_offset.  dcl != 0 removes the positive from the denominator (:834-836).
  * fwd:  lse[r] = log sum_c exp(s[r,c]);  pos[r] = s[r, r+diag_offset];
  *       *loss_accum += loss_scale * sum_r (lse[r] - pos[r])     (loss_accum may be NULL)
  *       part_ws: f32 scratch [xclip_nce_num_col_blocks(C) * R].
  *       (the reference's +1e-20 inside its logs, :51-52, is below fp32 resolution here)
- * bwd:  g[r,c] = w_row*exp(s - lse_row[r]) + w_col*exp(s - lse_col[c]) - w_diag*[c == r+diag]
- *       (exp terms skipped on the positive when dcl), written bf16 [R, ldg>=roundup8(C)];
- *       *dtemp += sum g*s (d loss / d temperature parameter) when dtemp != NULL.
- *       The latent gradient is then  dA = temp_exp * g @ b  via xclip_gemm_bf16. */
+ * bwd:  g[r,c] = *gscale * (w_row*exp(s - lse_row[r]) + w_col*exp(s - lse_col[c])
+ *                           - w_diag*[c == r+diag])     (gscale: DEVICE scalar, upstream grad
+ *       / (2*B_global); exp terms skipped on the positive when dcl).  Written as
+ *       bf16 temp_exp*g [R, ldg>=roundup8(C)], so the latent gradient is dA = (that) @ b via
+ *       xclip_gemm_bf16;  *dtemp += sum g*s (d loss / d temperature) when dtemp != NULL. */
 int xclip_nce_num_col_blocks(int C);
-int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D, float temp_exp,
+int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D, const float* temp_exp,
                   int diag_offset, int dcl, float* part_ws, float* pos, float* lse,
                   float* loss_accum, float loss_scale, xclip_stream_t stream);
-int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, float temp_exp,
+int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, const float* temp_exp,
                   int diag_offset, int dcl, const float* lse_row, const float* lse_col,
-                  float w_row, float w_col, float w_diag, void* g, int64_t ldg, float* dtemp,
-                  xclip_stream_t stream);
+                  float w_row, float w_col, float w_diag, const float* gscale, void* g,
+                  int64_t ldg, float* dtemp, xclip_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,78 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: shard placement of the single latent
+all-gather, the (lse,pos) exchange and the global-loss assembly the ranks derive from it."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import clip_oracle as O
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from x_clip_b200 import distributed as D
+    assert D.world() == (rank, world)
+    b, dim = 3, 8
+    g = torch.Generator().manual_seed(0)
+    full = [torch.nn.functional.normalize(torch.randn(world * b, dim, generator=g), dim=-1) for _ in range(4)]
+    shards = [f[rank * b:(rank + 1) * b].clone() for f in full]
+    got = D.gather_rows(shards)
+    ok = all(torch.equal(a, f) for a, f in zip(got, full))
+
+    # each rank evaluates only its row block; the gathered (lse,pos) give the reference's global loss
+    temp = torch.tensor(1.0).exp()
+    zt, zi = got[0], got[1]
+    s_rows = temp * shards[0] @ zi.t()                       # local texts vs all images
+    s_cols = temp * shards[1] @ zt.t()                       # local images vs all texts
+    idx = torch.arange(b) + rank * b
+    stats = torch.stack([torch.logsumexp(s_rows, -1), s_rows[torch.arange(b), idx],
+                         torch.logsumexp(s_cols, -1), s_cols[torch.arange(b), idx]])
+    gs = D.gather_stats(stats)
+    loss = ((gs[0] - gs[1]).sum() + (gs[2] - gs[3]).sum()) / (2 * world * b)
+    cfg = O.ClipConfig()
+    ref = O.contrastive_loss(full[0], full[1], full[0], full[1], torch.tensor(1.0), cfg)
+    t = torch.ones(1) * (rank + 1)
+    D.all_reduce_sum_(t)
+    q.put((rank, ok, abs(loss.item() - ref.item()), t.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_and_loss_assembly():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29733, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = []
+    import queue as _q, time as _t
+    t0 = _t.time()
+    while len(res) < world and _t.time() - t0 < 240:
+        try:
+            res.append(q.get(timeout=2))
+        except _q.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    for p in procs:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    assert len(res) == world, "a rank died (see its traceback above)"
+    res.sort()
+    for rank, ok, err, red in res:
+        assert ok, f"rank {rank}: gathered rows are not in rank order"
+        assert err < 1e-6, f"rank {rank}: assembled loss differs from the full-batch loss by {err}"
+        assert red == 3.0
+
+
+def test_single_process_is_passthrough():
+    from x_clip_b200 import distributed as D
+    assert D.world() == (0, 1)
+    a = torch.randn(4, 8)
+    assert torch.equal(D.gather_rows([a])[0], a)
+    assert D.gather_stats(a) is a

@@ -1,0 +1,112 @@
+"""End-to-end parity of x_clip_b200.CLIP on the GPU against (a) the committed golden values
+produced by the reference and (b) the CPU oracle run live on the same protocol weights/inputs.
+
+Tolerances (bf16 MMA operands/activations, fp32 accumulation/statistics/loss; compared with the
+fp32 reference): loss rel-err <= 1e-3 (north star); latents cosine >= 0.999; d temperature within
+1e-2 relative (+1e-4 absolute: it is a difference of O(1) terms); global grad-norm rel <= 1e-2;
+per-parameter gradient cosine >= 0.99 for every tensor with a non-negligible gradient."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+TINY_CASES = ["tiny_plain", "tiny_nomask", "tiny_dcl", "tiny_extra", "tiny_dcl_extra", "tiny_patchdrop"]
+
+
+def _run(case, dev):
+    from oracle import clip_oracle as O
+    import x_clip_b200
+    gold = json.loads((GOLD / f"{case}.json").read_text())
+    cfg = O.ClipConfig(**gold["cfg"])
+    state = O.protocol_state_dict(cfg, gold["weight_seed"])
+    text, image = O.protocol_inputs(cfg, gold["batch"], gold["input_seed"], gold["pad_fraction"])
+    keep = None if gold["keep"] is None else torch.tensor(gold["keep"])
+
+    clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=gold["patch_dropout"]).to(dev)
+    clip.load_state_dict(state, strict=True)
+    clip.train()
+    if keep is not None:
+        clip.visual_transformer.patch_dropout.forced_keep = keep
+    loss = clip(text.to(dev), image.to(dev), return_loss=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().float().cpu() for k, p in clip.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        lat = clip(text.to(dev), image.to(dev), return_latents=True)
+
+    # oracle, live, fp32 CPU
+    p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    o_loss = O.clip_forward(p, text, image, cfg, keep=keep)
+    o_loss.backward()
+    return gold, loss.item(), grads, [z.float().cpu() for z in lat], o_loss.item(), p
+
+
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_clip_matches_reference(cuda_device, case):
+    gold, loss, grads, lat, o_loss, p = _run(case, cuda_device)
+    assert abs(o_loss - gold["loss"]) < 1e-5            # oracle == reference (pinned on CPU too)
+    rel = abs(loss - gold["loss"]) / abs(gold["loss"])
+    assert rel <= 1e-3, f"loss {loss} vs reference {gold['loss']} (rel {rel:.2e})"
+
+    zt_ref = torch.tensor(gold["text_latents"])
+    zi_ref = torch.tensor(gold["image_latents"])
+    for z, ref, name in ((lat[0], zt_ref, "text"), (lat[1], zi_ref, "image")):
+        cos = torch.nn.functional.cosine_similarity(z, ref, dim=-1).min().item()
+        assert cos >= 0.999, f"{name} latents cosine {cos}"
+
+    dt = grads["temperature"].item()
+    assert abs(dt - gold["dtemperature"]) <= 1e-2 * abs(gold["dtemperature"]) + 1e-4, (dt, gold["dtemperature"])
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+    assert abs(gn - gold["grad_norm"]) <= 1e-2 * gold["grad_norm"], (gn, gold["grad_norm"])
+
+    bad = []
+    for k, g in grads.items():
+        og = p[k].grad
+        if og is None or og.norm().item() < 1e-3 * gold["grad_norm"]:
+            continue
+        cos = torch.nn.functional.cosine_similarity(g.flatten().double(), og.flatten().double(), dim=0).item()
+        nrel = abs(g.norm().item() - og.norm().item()) / og.norm().item()
+        if cos < 0.99 or nrel > 5e-2:
+            bad.append((k, round(cos, 4), round(nrel, 4)))
+    assert not bad, bad
+
+
+def test_readme_config_matches_reference(cuda_device):
+    """cfg1 (README model, B=4): the configuration the reference itself can run on CPU."""
+    gold, loss, grads, lat, o_loss, p = _run("readme_plain", cuda_device)
+    rel = abs(loss - gold["loss"]) / abs(gold["loss"])
+    assert rel <= 1e-3, f"loss {loss} vs {gold['loss']} rel {rel:.2e}"
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+    assert abs(gn - gold["grad_norm"]) <= 1e-2 * gold["grad_norm"], (gn, gold["grad_norm"])
+    dt = grads["temperature"].item()
+    assert abs(dt - gold["dtemperature"]) <= 1e-2 * abs(gold["dtemperature"]) + 1e-4
+
+
+def test_state_dict_roundtrip_and_early_returns(cuda_device):
+    from oracle import clip_oracle as O
+    import x_clip_b200
+    gold = json.loads((GOLD / "tiny_extra.json").read_text())
+    cfg = O.ClipConfig(**gold["cfg"])
+    clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0.).to(cuda_device)
+    assert set(clip.state_dict().keys()) == set(O.param_shapes(cfg).keys())
+    for k, v in clip.state_dict().items():
+        assert tuple(v.shape) == O.param_shapes(cfg)[k], k
+    clip.load_state_dict(O.protocol_state_dict(cfg, 1234))
+    text, image = O.protocol_inputs(cfg, 4, 4321, 0.1)
+    text, image = text.to(cuda_device), image.to(cuda_device)
+    clip.eval()
+    with torch.no_grad():
+        et, ei = clip(text, image, return_encodings=True)
+        assert et.shape == (4, cfg.text_seq_len + 1, cfg.dim_text) and ei.shape[0] == 4
+        lat = clip(text, image, return_latents=True)
+        assert len(lat) == 4 and lat[0].shape == (4, cfg.dim_latent)
+        sim = clip(text, image)
+        assert sim.shape == (4,)
+        sim2 = clip(text, image, text_to_image=False)
+        assert sim2.shape == (4,)
+    with pytest.raises(AssertionError):
+        clip(text, image, return_loss=True)        # loss while .eval(), reference x_clip.py:651

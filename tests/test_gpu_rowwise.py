@@ -85,11 +85,16 @@ def test_l2norm(cuda_device, rows, d):
     from x_clip_b200 import kernels as K
     torch.manual_seed(3)
     p = torch.randn(rows, d, device=cuda_device)
-    z, z16, inv = K.l2norm_fwd(p)
+    z, zrow, zcol, inv = K.l2norm_fwd(p)
     pf = p.clone().requires_grad_(True)
     ref = torch.nn.functional.normalize(pf, dim=-1)
     assert torch.allclose(z, ref, atol=1e-6)
-    _close(z16, ref, 1e-2)
+    hi, lo = zrow[:, :d].float(), zrow[:, d:2 * d].float()
+    assert torch.equal(zrow[:, 2 * d:], zrow[:, :d]) and torch.equal(zcol[:, :2 * d], zrow[:, :d].repeat(1, 2))
+    assert torch.equal(zcol[:, 2 * d:], zrow[:, d:2 * d])
+    assert (hi + lo - ref.detach()).abs().max().item() < 2e-5          # split-bf16 carries ~16 bits
+    gram = zrow.float() @ zcol.float().t()
+    assert (gram - ref.detach() @ ref.detach().t()).abs().max().item() < 1e-4
     dz = torch.randn(rows, d, device=cuda_device)
     dp = K.l2norm_bwd(dz, z, inv)
     ref.backward(dz)

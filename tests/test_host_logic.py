@@ -1,0 +1,75 @@
+"""Host-side contract of the drop-in modules (no GPU): parameter tree, flags, error behaviour."""
+import pytest
+import torch
+
+import x_clip_b200
+from oracle import clip_oracle as O
+
+TINY = dict(dim_text=256, dim_image=256, dim_latent=256, num_text_tokens=128, text_enc_depth=2,
+            text_seq_len=16, text_heads=4, visual_enc_depth=2, visual_heads=4,
+            visual_image_size=64, visual_patch_size=16)
+
+
+def test_state_dict_matches_reference_names_and_shapes():
+    clip = x_clip_b200.CLIP(**TINY)
+    want = O.param_shapes(O.ClipConfig(**TINY))
+    got = {k: tuple(v.shape) for k, v in clip.state_dict().items()}
+    assert got == want
+    clip.load_state_dict(O.protocol_state_dict(O.ClipConfig(**TINY), 7), strict=True)
+
+
+def test_readme_config_parameter_count():
+    clip = x_clip_b200.CLIP(dim_text=512, dim_image=512, dim_latent=512, num_text_tokens=10000,
+                            text_enc_depth=6, text_seq_len=256, text_heads=8, visual_enc_depth=6,
+                            visual_image_size=256, visual_patch_size=32, visual_heads=8)
+    n = sum(p.numel() for p in clip.parameters())
+    assert abs(n - 58.5e6) < 0.1e6          # 58.5 M parameters
+    assert clip.temperature.item() == 1.0
+    assert torch.equal(clip.to_text_latent.weight, clip.to_text_latent_extra.weight)
+
+
+def test_unknown_kwargs_swallowed_and_asserts_kept():
+    x_clip_b200.CLIP(**TINY, some_future_flag=3)
+    with pytest.raises(AssertionError):
+        x_clip_b200.CLIP(**TINY, visual_has_cls_token=False, text_has_cls_token=False)
+    with pytest.raises(AssertionError):
+        x_clip_b200.CLIP(**TINY, text_causal_mask=True)          # eos id missing (x_clip.py:480)
+
+
+@pytest.mark.parametrize("kw", [dict(use_mlm=True), dict(use_visual_ssl=True), dict(text_rotary_pos_emb=True),
+                                dict(text_dim_head=32), dict(dim_text=320), dict(sim_reg_loss_weight=0.1),
+                                dict(downsample_image_embeds=True, use_all_token_embeds=True),
+                                dict(text_causal_mask=True, text_eos_id=1)])
+def test_unsupported_flags_raise_at_construction(kw):
+    with pytest.raises(x_clip_b200.Unsupported):
+        x_clip_b200.CLIP(**{**TINY, **kw})
+
+
+def test_cpu_inputs_fail_loudly():
+    clip = x_clip_b200.CLIP(**TINY)
+    text = torch.randint(0, 128, (2, 16))
+    img = torch.randn(2, 3, 64, 64)
+    with pytest.raises((x_clip_b200.Unsupported, RuntimeError)):
+        clip(text, img, return_loss=True)
+
+
+def test_pluggable_encoders_are_adopted():
+    class Enc(torch.nn.Module):
+        def forward(self, *a):
+            raise RuntimeError("not called here")
+    t, i = Enc(), Enc()
+    clip = x_clip_b200.CLIP(**TINY, text_encoder=t, image_encoder=i)
+    assert clip.text_transformer is t and clip.visual_transformer is i
+
+
+def test_patch_dropout_matches_reference_recipe():
+    pd = x_clip_b200.clip.PatchDropout(0.5)
+    pd.train()
+    x = torch.randn(3, 16, 8)
+    torch.manual_seed(5)
+    out = pd(x)
+    torch.manual_seed(5)
+    idx = torch.randn(3, 16).topk(8, dim=-1).indices          # x_clip.py:148-149
+    assert torch.equal(out, x[torch.arange(3)[:, None], idx])
+    pd.eval()
+    assert pd(x) is x

@@ -1,0 +1,397 @@
+"""Drop-in `CLIP` / `TextTransformer` / `VisionTransformer` for lucidrains/x-clip, B200 path.
+
+The constructor keywords, forward signature, early returns, assertions and - crucially -
+the parameter tree (`state_dict` keys and shapes) mirror the reference
+(x_clip/x_clip.py:295-390 and :412-875) so existing checkpoints and user code keep
+working.  The modules here are parameter CONTAINERS: all arithmetic on the hot path is
+done by the CUDA kernels behind include/xclip_b200.h, scheduled by x_clip_b200.engine.
+
+Feature combinations the kernels do not cover raise at construction (never a silent CPU or
+eager fallback): dim_head != 64, model dims not multiples of 256, rotary embeddings, causal
+text mask, dropout > 0, MLM / visual SSL / multiview / similarity-regularisation terms and
+conv-downsampled image latents.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import engine as E
+from . import kernels as K
+
+BF16 = torch.bfloat16
+
+
+class Unsupported(NotImplementedError):
+    pass
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise Unsupported("x_clip_b200: " + msg + " (no fallback path exists by design)")
+
+
+# ----------------------------------------------------------------------------- containers
+# The nesting below exists only to reproduce the reference's parameter names, e.g.
+# `transformer.layers.3.0.fn.to_out.1.g` or `to_tokens.1.weight`.
+
+class LayerNorm(nn.Module):
+    """gain-only LayerNorm parameter (reference :112-121)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(dim))
+
+
+class _Slot(nn.Module):
+    """Parameter-free placeholder keeping nn.Sequential indices aligned with the reference."""
+
+
+class PreNorm(nn.Module):
+    def __init__(self, dim: int, fn: nn.Module):
+        super().__init__()
+        self.norm = LayerNorm(dim)
+        self.fn = fn
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, dim_head: int = 64, heads: int = 8, causal: bool = False,
+                 dropout: float = 0.):
+        super().__init__()
+        _require(dim_head == 64, f"dim_head must be 64, got {dim_head}")
+        _require(not causal, "causal attention is not implemented (the reference path itself is "
+                             "broken, SURVEY.md 8c)")
+        _require(dropout == 0., "attention dropout > 0 is not implemented")
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        inner = dim_head * heads
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), LayerNorm(dim))
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int, mult: int = 4, dropout: float = 0.):
+        super().__init__()
+        _require(mult == 4, "feed-forward multiplier must be 4")
+        _require(dropout == 0., "feed-forward dropout > 0 is not implemented")
+        inner = dim * mult
+        self.net = nn.Sequential(
+            nn.Linear(dim, inner * 2, bias=False),   # value | gate
+            _Slot(),                                 # GEGLU
+            LayerNorm(inner),
+            _Slot(),                                 # Dropout(0)
+            nn.Linear(inner, dim, bias=False),
+        )
+
+
+class Transformer(nn.Module):
+    """norm_in -> depth x (attention, feed-forward) -> norm_out, executed by engine.TransformerFn."""
+
+    def __init__(self, dim: int, *, depth: int, dim_head: int = 64, heads: int = 8,
+                 causal: bool = False, attn_dropout: float = 0., ff_dropout: float = 0.,
+                 ff_mult: int = 4, checkpoint_during_training: bool = False):
+        super().__init__()
+        _require(dim % 256 == 0 and dim <= 1024, f"model dim must be 256/512/768/1024, got {dim}")
+        _require(depth >= 1, "depth must be >= 1")
+        self.dim, self.depth, self.heads = dim, depth, heads
+        # activation checkpointing only trades memory for recompute; accepted and ignored
+        self.checkpoint_during_training = checkpoint_during_training
+        self.layers = nn.ModuleList([
+            nn.ModuleList([
+                PreNorm(dim, Attention(dim, dim_head=dim_head, heads=heads, causal=causal,
+                                       dropout=attn_dropout)),
+                PreNorm(dim, FeedForward(dim, mult=ff_mult, dropout=ff_dropout)),
+            ]) for _ in range(depth)
+        ])
+        self.norm_in = LayerNorm(dim)
+        self.norm_out = LayerNorm(dim)
+
+    def flat_weights(self):
+        w = [self.norm_in.g, self.norm_out.g]
+        for attn, ff in self.layers:
+            w += [attn.norm.g, attn.fn.to_qkv.weight, attn.fn.to_out[0].weight, attn.fn.to_out[1].g,
+                  ff.norm.g, ff.fn.net[0].weight, ff.fn.net[2].g, ff.fn.net[4].weight]
+        return w
+
+    def forward(self, x, rotary_pos_emb=None, mask=None):
+        _require(rotary_pos_emb is None, "rotary position embedding is not implemented")
+        _require(x.is_cuda, "inputs must live on a CUDA (sm_100) device")
+        return E.TransformerFn.apply(x, mask, self.heads, self.depth, *self.flat_weights())
+
+
+class PatchDropout(nn.Module):
+    """Random patch keep (reference :134-151).  The indices are drawn with the same torch RNG
+    recipe (randn -> topk); tests may pin them through `forced_keep`."""
+
+    def __init__(self, prob: float):
+        super().__init__()
+        assert 0 <= prob < 1.
+        self.prob = prob
+        self.forced_keep: Optional[torch.Tensor] = None
+
+    def forward(self, x, force_keep_all: bool = False):
+        if not self.training or self.prob == 0. or force_keep_all:
+            return x
+        b, n, d = x.shape
+        keep = max(1, int(n * (1 - self.prob)))
+        if self.forced_keep is not None:
+            idx = self.forced_keep.to(x.device)
+        else:
+            idx = torch.randn(b, n, device=x.device).topk(keep, dim=-1).indices
+        return torch.gather(x, 1, idx[:, :, None].expand(-1, -1, d))
+
+
+class TextTransformer(nn.Module):
+    def __init__(self, dim: int, *, num_tokens: int, max_seq_len: int, dim_head: int,
+                 rotary_pos_emb=None, causal: bool = False, **kwargs):
+        super().__init__()
+        _require(not rotary_pos_emb, "text_rotary_pos_emb is not implemented")
+        _require(not causal, "text_causal_mask is not implemented")
+        self.token_emb = nn.Embedding(num_tokens, dim)
+        self.abs_pos_emb = nn.Embedding(max_seq_len, dim)
+        self.cls_token = nn.Parameter(torch.randn(dim))
+        self.transformer = Transformer(dim, dim_head=dim_head, causal=causal, **kwargs)
+
+    def forward(self, x, mask=None):
+        b, n = x.shape
+        tok = self.token_emb(x) + self.abs_pos_emb.weight[:n]
+        cls = self.cls_token.expand(b, 1, -1)
+        h = torch.cat((cls, tok), dim=1).to(BF16)
+        if mask is not None:
+            mask = torch.cat((torch.ones(b, 1, dtype=torch.bool, device=mask.device), mask), dim=1)
+        return self.transformer(h, mask=mask)
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, dim: int, *, image_size: int, patch_size: int, channels: int,
+                 patch_dropout: float = 0.5, **kwargs):
+        super().__init__()
+        assert image_size % patch_size == 0, 'Image dimensions must be divisible by the patch size.'
+        self.patch_size = patch_size
+        num_patches = (image_size // patch_size) ** 2
+        patch_dim = channels * patch_size ** 2
+        _require(patch_dim % 8 == 0, "channels * patch_size^2 must be a multiple of 8")
+        self.to_tokens = nn.Sequential(_Slot(), nn.Linear(patch_dim, dim))
+        self.pos_emb = nn.Embedding(num_patches, dim)
+        self.patch_dropout = PatchDropout(patch_dropout)
+        self.transformer = Transformer(dim, **kwargs)
+        self.to_cls_tokens = nn.Sequential(_Slot(), nn.Linear(dim, dim, bias=False), _Slot())
+
+    def patchify(self, img: torch.Tensor) -> torch.Tensor:
+        """[b, c, H, W] -> bf16 [b * (H/p)*(W/p), p*p*c] with the reference's (p1 p2 c) order."""
+        b, c, H, W = img.shape
+        p = self.patch_size
+        x = img.to(BF16).view(b, c, H // p, p, W // p, p).permute(0, 2, 4, 3, 5, 1)
+        return x.reshape(b * (H // p) * (W // p), p * p * c)
+
+    def forward(self, x, keep_all_patches: bool = False):
+        b = x.shape[0]
+        lin = self.to_tokens[1]
+        patches = self.patchify(x)
+        n = patches.shape[0] // b
+        _require(n == self.pos_emb.num_embeddings, "image size does not match the position table")
+        tok = E.LinearFn.apply(patches, lin.weight, lin.bias, self.pos_emb.weight)
+        tok = tok.view(b, n, -1)
+        tok = self.patch_dropout(tok, force_keep_all=keep_all_patches)
+        out = self.transformer(tok)
+        pooled = out.float().mean(dim=1).to(BF16)
+        cls = E.LinearFn.apply(pooled, self.to_cls_tokens[1].weight, None, None)
+        return torch.cat((cls[:, None], out), dim=1)
+
+
+# ----------------------------------------------------------------------------- CLIP
+
+def _encode(fn, args, freeze: bool):
+    if not freeze:
+        return fn(*args)
+    with torch.no_grad():
+        return fn(*args).detach()
+
+
+class CLIP(nn.Module):
+    def __init__(
+        self,
+        *,
+        image_encoder=None,
+        text_encoder=None,
+        dim_text=512,
+        dim_image=512,
+        dim_latent=512,
+        num_text_tokens=10000,
+        text_enc_depth=6,
+        text_seq_len=256,
+        text_heads=8,
+        text_dim_head=64,
+        text_has_cls_token=True,
+        text_pad_id=0,
+        text_rotary_pos_emb=False,
+        text_causal_mask=False,
+        text_eos_id=None,
+        text_encode_without_mask=False,
+        visual_enc_depth=6,
+        visual_heads=8,
+        visual_dim_head=64,
+        visual_image_size=256,
+        visual_patch_size=32,
+        visual_patch_dropout=0.5,
+        visual_has_cls_token=True,
+        channels=3,
+        use_all_token_embeds=False,
+        downsample_image_embeds=False,
+        decoupled_contrastive_learning=False,
+        extra_latent_projection=False,
+        use_mlm=False,
+        text_ssl_loss_weight=0.05,
+        use_visual_ssl=False,
+        visual_ssl=None,
+        visual_ssl_type='simsiam',
+        visual_ssl_hidden_layer=-1,
+        simclr_temperature=0.1,
+        image_ssl_loss_weight=0.05,
+        multiview_loss_weight=0.1,
+        checkpoint_during_training=False,
+        sim_reg_loss_weight=0.,
+        **kwargs,     # unknown keywords are swallowed, like the reference (:455)
+    ):
+        super().__init__()
+        assert use_all_token_embeds or (visual_has_cls_token or text_has_cls_token), \
+            'CLS token must be included on both vision and text transformers if you are not using fine-grained contrastive learning loss'
+        assert not (text_causal_mask and text_eos_id is None), \
+            'text EOS token id must be given if using causal mask in text transformer'
+        _require(not use_mlm, "use_mlm (MLM auxiliary loss) is outside the accelerated hot path")
+        _require(not (use_visual_ssl or visual_ssl is not None),
+                 "visual SSL (SimSiam/SimCLR) is outside the accelerated hot path")
+        _require(not downsample_image_embeds, "downsample_image_embeds is not implemented")
+        _require(sim_reg_loss_weight == 0., "sim_reg_loss_weight > 0 is not implemented")
+        _require(not text_causal_mask, "text_causal_mask is not implemented")
+        _require(dim_latent % 256 == 0 and dim_latent <= 1024, "dim_latent must be 256/512/768/1024")
+        _require(dim_text % 8 == 0 and dim_image % 8 == 0, "dim_text / dim_image must be multiples of 8")
+
+        self.dim_text, self.dim_image, self.dim_latent = dim_text, dim_image, dim_latent
+        self.image_channels = channels
+        self.image_size = visual_image_size
+        self.text_pad_id = text_pad_id
+        self.text_has_cls_token = text_has_cls_token
+        self.text_seq_len = text_seq_len
+        self.text_encode_without_mask = text_encode_without_mask
+        self.text_causal_mask = text_causal_mask
+        self.text_eos_id = text_eos_id
+        self.visual_has_cls_token = visual_has_cls_token
+
+        if text_encoder is not None:
+            self.text_transformer = text_encoder
+        else:
+            self.text_transformer = TextTransformer(
+                dim=dim_text, num_tokens=num_text_tokens, max_seq_len=text_seq_len,
+                depth=text_enc_depth, heads=text_heads, causal=text_causal_mask,
+                dim_head=text_dim_head, rotary_pos_emb=text_rotary_pos_emb,
+                checkpoint_during_training=checkpoint_during_training)
+
+        if image_encoder is not None:
+            self.visual_transformer = image_encoder
+        else:
+            self.visual_transformer = VisionTransformer(
+                dim=dim_image, image_size=visual_image_size, patch_size=visual_patch_size,
+                channels=channels, depth=visual_enc_depth, heads=visual_heads,
+                dim_head=visual_dim_head, patch_dropout=visual_patch_dropout,
+                checkpoint_during_training=checkpoint_during_training)
+
+        self.use_mlm = False
+        self.use_visual_ssl = False
+        self.text_ssl_loss_weight = 0
+        self.image_ssl_loss_weight = 0
+
+        self.to_text_latent = nn.Linear(dim_text, dim_latent, bias=False)
+        self.to_visual_latent = nn.Linear(dim_image, dim_latent, bias=False)
+        self.temperature = nn.Parameter(torch.tensor(1.))
+
+        self.use_all_token_embeds = use_all_token_embeds
+        self.decoupled_contrastive_learning = decoupled_contrastive_learning
+        self.extra_latent_projection = extra_latent_projection
+        # always present, initialised as copies, exactly like the reference (:585-586)
+        self.to_text_latent_extra = copy.deepcopy(self.to_text_latent)
+        self.to_visual_latent_extra = copy.deepcopy(self.to_visual_latent)
+
+        self.multiview_loss_weight = multiview_loss_weight
+        # latched at construction, like the reference (:591): the process group must exist first
+        self.requires_all_gather = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.sim_reg_loss_weight = sim_reg_loss_weight
+        self.has_sim_reg_loss = False
+
+    # -- helpers ---------------------------------------------------------------------
+    def _project(self, embeds: torch.Tensor, linear: nn.Linear):
+        """embeds [..., d] (any float dtype) -> (z fp32 [..., D], (zrow, zcol) bf16 [rows, 3D])."""
+        lead = embeds.shape[:-1]
+        e = embeds.reshape(-1, embeds.shape[-1])
+        if e.dtype != BF16:
+            e = e.to(BF16)
+        z, zrow, zcol = E.ProjectL2NormFn.apply(e, linear.weight)
+        return z.view(*lead, -1), (zrow, zcol)
+
+    def forward(
+        self,
+        text,
+        image,
+        return_loss=False,
+        return_encodings=False,
+        return_latents=False,
+        freeze_image_encoder=False,
+        freeze_text_encoder=False,
+        text_to_image=True,
+        aug_text=None,
+        aug_image=None,
+    ):
+        _require(aug_text is None and aug_image is None, "multiview (aug_text/aug_image) is not implemented")
+        assert not (return_loss and not self.training), 'loss cannot be used if not training'
+        _require(text.is_cuda and image.is_cuda, "inputs must live on a CUDA (sm_100) device")
+
+        text_mask = text != self.text_pad_id
+        text_args = (text,) if self.text_encode_without_mask else (text, text_mask)
+        enc_text = _encode(self.text_transformer, text_args, freeze_text_encoder)
+        enc_image = _encode(self.visual_transformer, (image,), freeze_image_encoder)
+
+        if return_encodings:
+            return enc_text.float(), enc_image.float()
+
+        if self.use_all_token_embeds:
+            assert enc_text.ndim == 3, 'encoded text must have 3 dimensions (batch, seq, features)'
+            assert enc_image.ndim == 3, 'encoded image must have 3 dimensions (batch, seq [height x width], features)'
+            text_embeds = enc_text[:, 1:] if self.text_has_cls_token else enc_text
+            image_embeds = enc_image[:, 1:] if self.visual_has_cls_token else enc_image
+        else:
+            text_embeds = enc_text[:, 0] if enc_text.ndim == 3 else enc_text
+            image_embeds = enc_image[:, 0] if enc_image.ndim == 3 else enc_image
+
+        zt, ops_t = self._project(text_embeds, self.to_text_latent)
+        zi, ops_i = self._project(image_embeds, self.to_visual_latent)
+        zt_x, zi_x = zt, zi
+        ops = [ops_t, ops_i]
+        if self.extra_latent_projection:
+            zt_x, ops_tx = self._project(text_embeds, self.to_text_latent_extra)
+            zi_x, ops_ix = self._project(image_embeds, self.to_visual_latent_extra)
+            ops += [ops_tx, ops_ix]
+
+        if return_latents:
+            if self.extra_latent_projection:
+                return zt, zi, zt_x, zi_x
+            return zt, zi
+
+        if not return_loss:
+            temp = self.temperature.exp()
+            a, b = (zt_x, zi_x) if (self.extra_latent_projection and not text_to_image) else (zt, zi)
+            if self.use_all_token_embeds:
+                return torch.einsum('btd,bid->bti', a, b) * temp      # per-pair token sims (:740-742)
+            return (a * b).sum(dim=-1) * temp                          # per-pair similarity (:744-746)
+
+        if self.use_all_token_embeds:
+            from .filip import filip_loss
+            return filip_loss(self, zt, zi, zt_x, zi_x, text_mask)
+
+        return E.ContrastiveLossFn.apply(
+            zt, zi, zt_x if self.extra_latent_projection else None,
+            zi_x if self.extra_latent_projection else None, self.temperature,
+            tuple(ops), self.decoupled_contrastive_learning, self.requires_all_gather)

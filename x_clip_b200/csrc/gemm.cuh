@@ -44,6 +44,8 @@ struct GemmParams {
   const float* lse_col;  // BWD: [N]  log-denominator of each column (other direction)
   float w_row, w_col, w_diag;
   float* dtemp;          // BWD: scalar accumulator of sum(g * s) or null
+  const float* alpha_dev;  // NCE: exp(temperature) read from device memory (no host sync)
+  const float* gscale_dev; // BWD: upstream scalar gradient / (2*B_global), multiplies the weights
 };
 
 constexpr int EPI_STORE = 0;    // C = alpha*acc (+bias) (+residual)
@@ -286,7 +288,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else if constexpr (EPI == EPI_NCE_FWD) {
         // s = alpha*acc with |s| <= alpha (unit-norm latents): exp(s - alpha) cannot overflow.
-        const float a2 = p.alpha * 1.4426950408889634f;
+        const float alpha = __ldg(p.alpha_dev);
+        const float a2 = alpha * 1.4426950408889634f;
         const int diag_col = row + p.diag_offset;
         float rsum = 0.f;
 #pragma unroll 1
@@ -300,13 +303,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int col = col0 + i;
             const float acc_v = __uint_as_float(v[i]);
             const bool is_diag = (col == diag_col);
-            if (is_diag && row_ok) p.nce_pos[row] = acc_v * p.alpha;
+            if (is_diag && row_ok) p.nce_pos[row] = acc_v * alpha;
             if (col < p.N && !(p.dcl && is_diag)) rsum += exp2f(acc_v * a2 - a2);
           }
         }
         if (row_ok) p.nce_part[(long long)n_blk * p.M + row] = rsum;
       } else {
-        const float a2 = p.alpha * 1.4426950408889634f;
+        const float alpha = __ldg(p.alpha_dev);
+        const float gs = __ldg(p.gscale_dev);
+        const float w_row = p.w_row * gs, w_col = p.w_col * gs, w_diag = p.w_diag * gs;
+        const float a2 = alpha * 1.4426950408889634f;
         const int diag_col = row + p.diag_offset;
         const float lr2 = (row_ok && p.lse_row) ? p.lse_row[row] * 1.4426950408889634f : 0.f;
         float tsum = 0.f;
@@ -326,14 +332,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float gv = 0.f;
               if (col < p.N) {
                 if (!(p.dcl && is_diag)) {
-                  if (p.w_row != 0.f) gv += p.w_row * exp2f(acc_v * a2 - lr2);
+                  if (p.w_row != 0.f) gv += w_row * exp2f(acc_v * a2 - lr2);
                   if (p.w_col != 0.f)
-                    gv += p.w_col * exp2f(acc_v * a2 - p.lse_col[col] * 1.4426950408889634f);
+                    gv += w_col * exp2f(acc_v * a2 - p.lse_col[col] * 1.4426950408889634f);
                 }
-                if (is_diag) gv -= p.w_diag;
-                tsum += gv * acc_v * p.alpha;
+                if (is_diag) gv -= w_diag;
+                tsum += gv * acc_v * alpha;
               }
-              gq[i] = gv;
+              gq[i] = gv * alpha;   // temperature folded in: d rows = gq @ cols
             }
             bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll

@@ -20,9 +20,10 @@ namespace xclip {
 
 __global__ void __launch_bounds__(1024)
 nce_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ pos,
-                    int rows, float alpha, float* __restrict__ lse, float* __restrict__ loss_accum,
-                    float scale) {
+                    int rows, const float* __restrict__ alpha_dev, float* __restrict__ lse,
+                    float* __restrict__ loss_accum, float scale) {
   __shared__ float red[32];
+  const float alpha = __ldg(alpha_dev);
   float local = 0.f;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -84,7 +85,8 @@ using namespace xclip;
 
 extern "C" int xclip_nce_num_col_blocks(int C) { return C >= 256 ? (C + 255) / 256 : (C + 127) / 128; }
 
-extern "C" int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D, float temp_exp,
+extern "C" int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D,
+                             const float* temp_exp,
                              int diag_offset, int dcl, float* part_ws, float* pos, float* lse,
                              float* loss_accum, float loss_scale, xclip_stream_t stream) {
   GemmParams p;
@@ -92,9 +94,9 @@ extern "C" int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D, 
   int block_n = 0, grid = 0;
   int rc = nce_common(a, b, R, C, D, &p, &tmA, &tmB, &block_n, &grid);
   if (rc) return rc;
-  XCLIP_REQUIRE(part_ws && pos && lse, "nce_fwd: null workspace/output");
+  XCLIP_REQUIRE(part_ws && pos && lse && temp_exp, "nce_fwd: null workspace/output");
   XCLIP_REQUIRE(diag_offset >= 0 && diag_offset + R <= C, "nce_fwd: positives outside the columns");
-  p.alpha = temp_exp; p.diag_offset = diag_offset; p.dcl = dcl;
+  p.alpha_dev = temp_exp; p.diag_offset = diag_offset; p.dcl = dcl;
   p.nce_part = part_ws; p.nce_pos = pos;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   rc = block_n == 256 ? launch_nce<256, EPI_NCE_FWD>(tmA, tmB, p, grid, s)
@@ -109,9 +111,10 @@ extern "C" int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D, 
   return XCLIP_OK;
 }
 
-extern "C" int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, float temp_exp,
-                             int diag_offset, int dcl, const float* lse_row, const float* lse_col,
-                             float w_row, float w_col, float w_diag, void* g, int64_t ldg,
+extern "C" int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D,
+                             const float* temp_exp, int diag_offset, int dcl,
+                             const float* lse_row, const float* lse_col, float w_row, float w_col,
+                             float w_diag, const float* gscale, void* g, int64_t ldg,
                              float* dtemp, xclip_stream_t stream) {
   GemmParams p;
   CUtensorMap tmA, tmB;
@@ -121,7 +124,8 @@ extern "C" int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, 
   XCLIP_REQUIRE(g && ldg % 8 == 0 && ldg >= (C + 7) / 8 * 8, "nce_bwd: g needs ld >= roundup8(C)");
   XCLIP_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "nce_bwd: misaligned g");
   XCLIP_REQUIRE((w_row == 0.f || lse_row) && (w_col == 0.f || lse_col), "nce_bwd: missing lse");
-  p.alpha = temp_exp; p.diag_offset = diag_offset; p.dcl = dcl;
+  XCLIP_REQUIRE(temp_exp && gscale, "nce_bwd: temp_exp / gscale device scalars required");
+  p.alpha_dev = temp_exp; p.gscale_dev = gscale; p.diag_offset = diag_offset; p.dcl = dcl;
   p.lse_row = lse_row; p.lse_col = lse_col;
   p.w_row = w_row; p.w_col = w_col; p.w_diag = w_diag;
   p.c = g; p.ldc = ldg; p.dtemp = dtemp;

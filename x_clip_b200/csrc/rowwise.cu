@@ -333,13 +333,16 @@ geglu_ln_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __r
 
 // ---------------------------------------------------------------------------
 // l2-normalise rows of an fp32 matrix: z = p / max(||p||, 1e-12)
-//   fwd writes z (fp32), z16 (bf16, operand of the logits MMA) and inv = 1/max(||p||,eps)
+//   fwd writes z (fp32), the split-bf16 MMA operands zrow = [hi|lo|hi], zcol = [hi|hi|lo]
+//   ([rows, 3d] each; zrow . zcol^T reproduces the fp32 dot product to ~2^-17) and
+//   inv = 1/max(||p||,eps)
 //   bwd: dp = inv * (dz - z * <z, dz>)   (bf16, operand of the projection dgrad/wgrad)
 // ---------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
 l2norm_fwd_kernel(const float* __restrict__ p, long long ldp, float* __restrict__ z,
-                  bf16* __restrict__ z16, float* __restrict__ inv, int rows) {
+                  bf16* __restrict__ zrow, bf16* __restrict__ zcol, float* __restrict__ inv,
+                  int rows) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int warp_stride = gridDim.x * kRowWarps;
@@ -358,10 +361,19 @@ l2norm_fwd_kernel(const float* __restrict__ p, long long ldp, float* __restrict_
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int col = (j * 32 + lane) * 8;
+      float hi[8], lo[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[j][e] *= r;
+      for (int e = 0; e < 8; ++e) {
+        v[j][e] *= r;
+        hi[e] = bf16_round(v[j][e]);
+        lo[e] = v[j][e] - hi[e];
+      }
       storef8(z + (long long)row * D + col, v[j]);
-      store8(z16 + (long long)row * D + col, v[j]);
+      // split-bf16 operands: <a,b> ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (error ~2^-17)
+      bf16* zr = zrow + (long long)row * (3 * D);
+      bf16* zc = zcol + (long long)row * (3 * D);
+      store8(zr + col, hi); store8(zr + D + col, lo); store8(zr + 2 * D + col, hi);
+      store8(zc + col, hi); store8(zc + D + col, hi); store8(zc + 2 * D + col, lo);
     }
   }
 }
@@ -532,16 +544,17 @@ extern "C" int xclip_geglu_ln_bwd(const void* dh_, int64_t lddh, const void* u, 
   return XCLIP_OK;
 }
 
-extern "C" int xclip_l2norm_fwd(const float* p, int64_t ldp, float* z, void* z16, float* inv,
-                                int rows, int d, xclip_stream_t stream) {
+extern "C" int xclip_l2norm_fwd(const float* p, int64_t ldp, float* z, void* zrow, void* zcol,
+                                float* inv, int rows, int d, xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
-  XCLIP_REQUIRE(p && z && z16 && inv, "l2norm_fwd: null pointer");
+  XCLIP_REQUIRE(p && z && zrow && zcol && inv, "l2norm_fwd: null pointer");
   XCLIP_REQUIRE(rows > 0 && d % 256 == 0, "l2norm_fwd: rows=%d d=%d", rows, d);
-  XCLIP_REQUIRE(ldp % 4 == 0 && ALIGNED16(p) && ALIGNED16(z) && ALIGNED16(z16),
+  XCLIP_REQUIRE(ldp % 4 == 0 && ALIGNED16(p) && ALIGNED16(z) && ALIGNED16(zrow) && ALIGNED16(zcol),
                 "l2norm_fwd: misaligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NARROW(l2norm_fwd_kernel, d, row_grid(rows), s, p, ldp, z, (bf16*)z16, inv, rows)
+  DISPATCH_NARROW(l2norm_fwd_kernel, d, row_grid(rows), s, p, ldp, z, (bf16*)zrow, (bf16*)zcol,
+                  inv, rows)
   XCLIP_LAUNCH_CHECK("l2norm_fwd_kernel");
   return XCLIP_OK;
 }

@@ -1,0 +1,290 @@
+"""Forward/backward schedules of the hot path as torch.autograd.Functions.
+
+Each Function is a hand-written schedule of C-ABI kernel calls (x_clip_b200.kernels);
+autograd only stitches them to the few torch ops left around them (embedding gather,
+patchify, patch-dropout gather).  Activations are bf16, accumulation/statistics fp32,
+parameters stay fp32 in the modules (state_dict compatible with the reference) and are
+cast to bf16 once per step.
+
+Reference call sites: Transformer.forward x_clip/x_clip.py:274-291 (TransformerFn),
+nn.Linear :358,:368 (LinearFn), :713-724 (ProjectL2NormFn), :759-769 + :797-847
+(ContrastiveLossFn, with x_clip/distributed.py:41-56 for the gather contract).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from . import distributed as D_
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+LN_EPS = 1e-5   # the reference's fp32 branch (x_clip.py:118); parameters/outputs are fp32-facing
+
+_bf16_cache = {}
+
+
+def weight_bf16(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 parameter, cached until the parameter is modified in place."""
+    key = id(p)
+    ver = p._version
+    hit = _bf16_cache.get(key)
+    if hit is not None and hit[0] == ver and hit[1] == p.data_ptr():
+        return hit[2]
+    w = K.cast_bf16(p.detach())
+    _bf16_cache[key] = (ver, p.data_ptr(), w)
+    return w
+
+
+def clear_weight_cache() -> None:
+    _bf16_cache.clear()
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW[out,in] = dy^T @ x in fp32: both operands consumed MN-major, split-K + atomics."""
+    out = torch.zeros((dy.shape[1], x.shape[1]), device=dy.device, dtype=F32)
+    K.gemm(dy, x, a_major=1, b_major=1, out=out, accumulate=True)
+    return out
+
+
+class LayerWeights:
+    """fp32 parameters of one transformer layer, in the order TransformerFn receives them."""
+    FIELDS = ("g1", "wqkv", "wo", "go", "g2", "w1", "g4", "w2")
+
+
+class TransformerFn(torch.autograd.Function):
+    """x[B,n,d] (bf16) -> norm_out(blocks(norm_in(x))) (bf16); mask: bool [B,n] or None.
+
+    flat weights = [norm_in.g, norm_out.g] + depth * [g1, wqkv, wo, go, g2, w1, g4, w2].
+    """
+
+    @staticmethod
+    def forward(ctx, x, mask, heads: int, depth: int, *weights):
+        B, n, d = x.shape
+        M = B * n
+        scale = 64 ** -0.5
+        g_in, g_out = weights[0], weights[1]
+        layers = [weights[2 + 8 * L: 2 + 8 * (L + 1)] for L in range(depth)]
+        x_in = x.reshape(M, d)
+        if x_in.dtype != BF16:
+            x_in = x_in.to(BF16)
+        x_in = x_in.contiguous()
+        mask_c = None if mask is None else mask.contiguous()
+
+        saved = []
+        # norm_in fused with the first pre-norm
+        xcur, st_in, xn, st1 = K.layernorm_fwd(x_in, g_in, g2=layers[0][0], eps=LN_EPS)
+        for L, (g1, wqkv, wo, go, g2, w1, g4, w2) in enumerate(layers):
+            qkv = K.gemm(xn, weight_bf16(wqkv))
+            o, lse = K.attn_fwd(qkv, mask_c, B, n, heads, scale)
+            y = K.gemm(o, weight_bf16(wo))
+            # x1 = LN(y)*go + x ; xn2 = LN(x1)*g2   (attention tail + feed-forward pre-norm)
+            x1, st_y, xn2, st_x1 = K.layernorm_fwd(y, go, res=xcur, g2=g2, eps=LN_EPS)
+            u = K.gemm(xn2, weight_bf16(w1))
+            h, st_v = K.geglu_ln_fwd(u, g4, eps=LN_EPS)
+            x2 = K.gemm(h, weight_bf16(w2), residual=x1)
+            saved.append((xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h))
+            xcur = x2
+            if L + 1 < depth:
+                xn, st1, _, _ = K.layernorm_fwd(xcur, layers[L + 1][0], eps=LN_EPS)
+        out, st_out, _, _ = K.layernorm_fwd(xcur, g_out, eps=LN_EPS)
+
+        ctx.saved = saved
+        ctx.tail = (x_in, st_in, xcur, st_out)
+        ctx.mask = mask_c
+        ctx.dims = (B, n, d, heads, depth, scale)
+        ctx.weights = weights
+        return out.view(B, n, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, n, d, heads, depth, scale = ctx.dims
+        M = B * n
+        weights = ctx.weights
+        g_in, g_out = weights[0], weights[1]
+        layers = [weights[2 + 8 * L: 2 + 8 * (L + 1)] for L in range(depth)]
+        x_in, st_in, x_last, st_out = ctx.tail
+        dev = dout.device
+        dout = dout.reshape(M, d)
+        if dout.dtype != BF16:
+            dout = dout.to(BF16)
+        dout = dout.contiguous()
+
+        grads: List[Optional[torch.Tensor]] = [None] * len(weights)
+        dg_out = torch.zeros(d, device=dev, dtype=F32)
+        dx = K.layernorm_bwd(dout, x_last, st_out, g_out, dg=dg_out)
+        grads[1] = dg_out
+        for L in reversed(range(depth)):
+            g1, wqkv, wo, go, g2, w1, g4, w2 = layers[L]
+            xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h = ctx.saved[L]
+            ctx.saved[L] = None
+            base = 2 + 8 * L
+            # feed-forward: x2 = h @ w2^T + x1
+            dh = K.gemm(dx, weight_bf16(w2), b_major=1)
+            grads[base + 7] = _wgrad(dx, h)
+            dg4 = torch.zeros(g4.shape[0], device=dev, dtype=F32)
+            du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
+            grads[base + 6] = dg4
+            del dh
+            dxn2 = K.gemm(du, weight_bf16(w1), b_major=1)
+            grads[base + 5] = _wgrad(du, xn2)
+            del du
+            dg2 = torch.zeros(d, device=dev, dtype=F32)
+            dx1 = K.layernorm_bwd(dxn2, x1, st_x1, g2, add=dx, dg=dg2)
+            grads[base + 4] = dg2
+            # attention: x1 = LN(o @ wo^T) * go + x
+            dgo = torch.zeros(d, device=dev, dtype=F32)
+            dy = K.layernorm_bwd(dx1, y, st_y, go, dg=dgo)
+            grads[base + 3] = dgo
+            d_o = K.gemm(dy, weight_bf16(wo), b_major=1)
+            grads[base + 2] = _wgrad(dy, o)
+            dqkv = K.attn_bwd(qkv, ctx.mask, o, d_o, lse, B, n, heads, scale)
+            dxn = K.gemm(dqkv, weight_bf16(wqkv), b_major=1)
+            grads[base + 1] = _wgrad(dqkv, xn)
+            dg1 = torch.zeros(d, device=dev, dtype=F32)
+            dx = K.layernorm_bwd(dxn, xcur, st1, g1, add=dx1, dg=dg1)
+            grads[base + 0] = dg1
+        dg_in = torch.zeros(d, device=dev, dtype=F32)
+        dx_in = K.layernorm_bwd(dx, x_in, st_in, g_in, dg=dg_in)
+        grads[0] = dg_in
+        ctx.saved = None
+        return (dx_in.view(B, n, d), None, None, None, *grads)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T (+ bias) (+ table[row % period])  - x bf16 [M,K], W fp32 [N,K].
+
+    `table` is a positional-embedding table added per row modulo `period` (the vision
+    transformer's pos_emb, x_clip.py:382-383) fused in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, table):
+        x = x.contiguous()
+        tbl16 = None if table is None else K.cast_bf16(table.detach())
+        y = K.gemm(x, weight_bf16(weight), bias=None if bias is None else bias.detach(),
+                   residual=tbl16, res_row_mod=0 if table is None else table.shape[0])
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.period = None if table is None else table.shape[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != BF16:
+            dy = dy.to(BF16)
+        dx = K.gemm(dy, weight_bf16(weight), b_major=1) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dy, x)
+        db = dy.float().sum(dim=0) if ctx.has_bias else None
+        dt = None
+        if ctx.period is not None:
+            dt = dy.float().view(-1, ctx.period, dy.shape[1]).sum(dim=0)
+        return dx, dw, db, dt
+
+
+class ProjectL2NormFn(torch.autograd.Function):
+    """z = normalize(e @ W^T) (x_clip.py:713-715).  Returns (z fp32, zrow, zcol): the last two
+    are the split-bf16 MMA operands of the logits contraction (no grad), see xclip_l2norm_fwd."""
+
+    @staticmethod
+    def forward(ctx, e, weight):
+        e = e.contiguous()
+        p = K.gemm(e, weight_bf16(weight), out_dtype=F32)
+        z, zrow, zcol, inv = K.l2norm_fwd(p)
+        ctx.save_for_backward(e, weight, z, inv)
+        ctx.mark_non_differentiable(zrow, zcol)
+        return z, zrow, zcol
+
+    @staticmethod
+    def backward(ctx, dz, _a, _b):
+        e, weight, z, inv = ctx.saved_tensors
+        dp = K.l2norm_bwd(dz.contiguous().float(), z, inv)
+        de = K.gemm(dp, weight_bf16(weight), b_major=1) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dp, e)
+        return de, dw
+
+
+class ContrastiveLossFn(torch.autograd.Function):
+    """InfoNCE / DCL over all pairs of the GLOBAL batch (x_clip.py:759-769, :813-847).
+
+    Inputs: local unit-norm latents zt, zi [b, D] (fp32, carry the graph), optional extra pair,
+    the temperature parameter, and `ops`: per latent set the (zrow, zcol) split-bf16 operands.
+    With world size W > 1 one all-gather exchanges the column operands of every set (replacing
+    x_clip/distributed.py:14-39), each rank evaluates only its own row blocks, and a second tiny
+    all-gather exchanges (lse, pos) so every rank returns the same global loss.  Backward
+    reproduces AllGather.backward's contract (distributed.py:50-54): latent grads are
+    d loss / d(local latents); d temperature is the full-batch gradient on every rank."""
+
+    @staticmethod
+    def forward(ctx, zt, zi, zt_x, zi_x, temperature, ops, dcl: bool, use_gather: bool):
+        extra = len(ops) == 4
+        rank, world = D_.world() if use_gather else (0, 1)
+        b = ops[0][0].shape[0]
+        D = ops[0][0].shape[1] // 3
+        temp_exp = temperature.detach().float().exp().reshape(1)
+
+        rows = [o[0] for o in ops]                                  # local [b, 3D], [hi|lo|hi]
+        cols = D_.gather_rows([o[1] for o in ops]) if world > 1 else [o[1] for o in ops]
+        Bg = world * b
+        off = rank * b
+
+        # forward row blocks: texts vs all images; images vs all texts (extra latents if any)
+        T, I, TX, IX = 0, 1, 2, 3
+        lse_t, pos_t = K.nce_fwd(rows[T], cols[I], temp_exp, off, dcl)
+        if extra:
+            lse_i, pos_i = K.nce_fwd(rows[IX], cols[TX], temp_exp, off, dcl)
+        else:
+            lse_i, pos_i = K.nce_fwd(rows[I], cols[T], temp_exp, off, dcl)
+
+        stats = torch.stack([lse_t, pos_t, lse_i, pos_i])                      # [4, b]
+        gstats = D_.gather_stats(stats) if world > 1 else stats
+        loss = ((gstats[0] - gstats[1]).sum() + (gstats[2] - gstats[3]).sum()) / (2.0 * Bg)
+
+        ctx.cfg = (dcl, extra, rank, world, b, D, Bg, off)
+        ctx.temp_exp = temp_exp
+        ctx.rows, ctx.cols = rows, cols
+        ctx.lse = (lse_t, lse_i, gstats[0].contiguous(), gstats[2].contiguous())
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        dcl, extra, rank, world, b, D, Bg, off = ctx.cfg
+        temp_exp = ctx.temp_exp
+        rows, cols = ctx.rows, ctx.cols
+        lse_t, lse_i, lse_t_all, lse_i_all = ctx.lse
+        gscale = (gloss.detach().float() / (2.0 * Bg)).reshape(1)
+        dtemp = torch.zeros(1, device=gloss.device, dtype=F32)
+        T, I, TX, IX = 0, 1, 2, 3
+
+        def latent_grad(r, c, lse_row, lse_col, w_row, w_col, w_diag, want_dtemp):
+            g = K.nce_bwd(rows[r], cols[c], temp_exp, off, dcl, lse_row, lse_col, w_row, w_col,
+                          w_diag, gscale, dtemp if want_dtemp else None)
+            # d rows = (temp * g) @ cols_hi ; g is zero-padded to a multiple of 8 columns
+            return K.gemm(g, _pad_rows(cols[c][:, :D], g.shape[1]), b_major=1, out_dtype=F32)
+
+        if not extra:
+            dzt = latent_grad(T, I, lse_t, lse_i_all, 1.0, 1.0, 2.0, True)
+            dzi = latent_grad(I, T, lse_i, lse_t_all, 1.0, 1.0, 2.0, False)
+            dzt_x = dzi_x = None
+        else:
+            dzt = latent_grad(T, I, lse_t, None, 1.0, 0.0, 1.0, True)
+            dzi = latent_grad(I, T, None, lse_t_all, 0.0, 1.0, 1.0, False)
+            dzi_x = latent_grad(IX, TX, lse_i, None, 1.0, 0.0, 1.0, True)
+            dzt_x = latent_grad(TX, IX, None, lse_i_all, 0.0, 1.0, 1.0, False)
+        if world > 1:
+            D_.all_reduce_sum_(dtemp)       # every rank holds the full-batch d loss / d temperature
+        ctx.rows = ctx.cols = None
+        return (dzt, dzi, dzt_x, dzi_x, dtemp.reshape(()), None, None, None)
+
+
+def _pad_rows(m: torch.Tensor, rows: int) -> torch.Tensor:
+    """g has roundup8(C) columns; the matching operand needs that many rows (zeros beyond C)."""
+    if m.shape[0] == rows:
+        return m
+    out = torch.zeros((rows, m.shape[1]), device=m.device, dtype=m.dtype)
+    out[: m.shape[0]] = m
+    return out

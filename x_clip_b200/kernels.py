@@ -20,6 +20,48 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class Profiler:
+    """Optional per-launch timing (CUDA events on the launching stream) with the ALGORITHMIC
+    flops / bytes of each call, used by bench.py for the roofline line.  Off by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (family, flops, bytes, start_event, end_event)
+
+    def start(self):
+        self.records = []
+        self.enabled = True
+
+    def stop(self):
+        """-> {family: dict(calls, ms, flops, bytes)}"""
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, by, e0, e1 in self.records:
+            d = out.setdefault(fam, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        self.records = []
+        return out
+
+
+PROF = Profiler()
+
+
+def _call(family: str, flops: float, nbytes: float, name: str, *args) -> None:
+    if not PROF.enabled:
+        _lib.call(name, *args)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    PROF.records.append((family, flops, nbytes, e0, e1))
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -70,7 +112,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
     if residual is not None:
         _need(residual, BF16, "residual"); _rows2d(residual, "residual")
         ldr = residual.stride(0)
-    _lib.call("xclip_gemm_bf16", a.data_ptr(), a.stride(0), a_major, b.data_ptr(), b.stride(0),
+    fam = "gemm_wgrad" if (a_major == 1 and b_major == 1) else ("gemm_dgrad" if b_major == 1 else "gemm_fwd")
+    nbytes = 2.0 * (M * K + N * K) + M * N * out.element_size() + (M * N * 2 if residual is not None else 0)
+    _call(fam, 2.0 * M * N * K, nbytes, "xclip_gemm_bf16", a.data_ptr(), a.stride(0), a_major, b.data_ptr(), b.stride(0),
               b_major, out.data_ptr(), out.stride(0), 1 if out.dtype == F32 else 0, M, N, K,
               float(alpha), _ptr(bias), _ptr(residual), ldr, int(res_row_mod),
               1 if accumulate else 0, _stream())
@@ -83,7 +127,8 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     src = src.contiguous()
     dst = torch.empty(src.shape, device=src.device, dtype=BF16)
     if src.numel():
-        _lib.call("xclip_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+        _call("cast", 0.0, 6.0 * src.numel(), "xclip_cast_f32_bf16", src.data_ptr(), dst.data_ptr(),
+              src.numel(), _stream())
     return dst
 
 
@@ -100,7 +145,8 @@ def layernorm_fwd(x, g, *, res=None, g2=None, eps=1e-5, want_stats=True):
         stats2 = torch.empty((rows, 2), device=x.device, dtype=F32)
     if res is not None:
         _need(res, BF16, "res"); _rows2d(res, "res")
-    _lib.call("xclip_layernorm_fwd", x.data_ptr(), x.stride(0), g.data_ptr(), _ptr(res),
+    passes = 2 + (1 if res is not None else 0) + (1 if g2 is not None else 0)
+    _call("layernorm_fwd", 0.0, 2.0 * rows * d * passes, "xclip_layernorm_fwd", x.data_ptr(), x.stride(0), g.data_ptr(), _ptr(res),
               res.stride(0) if res is not None else 0, out.data_ptr(), out.stride(0), _ptr(stats),
               _ptr(g2), _ptr(out2), out2.stride(0) if out2 is not None else 0, _ptr(stats2),
               rows, d, float(eps), _stream())
@@ -114,7 +160,8 @@ def layernorm_bwd(dy, x, stats, g, *, add=None, dg=None):
     dx = torch.empty((rows, d), device=x.device, dtype=BF16)
     if add is not None:
         _need(add, BF16, "add"); _rows2d(add, "add")
-    _lib.call("xclip_layernorm_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
+    _call("layernorm_bwd", 0.0, 2.0 * rows * d * (3 + (1 if add is not None else 0)),
+          "xclip_layernorm_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
               stats.data_ptr(), g.data_ptr(), _ptr(add), add.stride(0) if add is not None else 0,
               dx.data_ptr(), dx.stride(0), _ptr(dg), rows, d, _stream())
     return dx
@@ -126,7 +173,7 @@ def geglu_ln_fwd(u, g, *, eps=1e-5):
     dh = two_dh // 2
     h = torch.empty((rows, dh), device=u.device, dtype=BF16)
     stats = torch.empty((rows, 2), device=u.device, dtype=F32)
-    _lib.call("xclip_geglu_ln_fwd", u.data_ptr(), u.stride(0), g.data_ptr(), h.data_ptr(),
+    _call("geglu_ln_fwd", 0.0, 2.0 * rows * dh * 3, "xclip_geglu_ln_fwd", u.data_ptr(), u.stride(0), g.data_ptr(), h.data_ptr(),
               h.stride(0), stats.data_ptr(), rows, dh, float(eps), _stream())
     return h, stats
 
@@ -135,7 +182,7 @@ def geglu_ln_bwd(dh_grad, u, stats, g, *, dg=None):
     _need(dh_grad, BF16, "dh"); _rows2d(dh_grad, "dh"); _need(u, BF16, "u")
     rows, two_dh = u.shape
     du = torch.empty((rows, two_dh), device=u.device, dtype=BF16)
-    _lib.call("xclip_geglu_ln_bwd", dh_grad.data_ptr(), dh_grad.stride(0), u.data_ptr(),
+    _call("geglu_ln_bwd", 0.0, 2.0 * rows * (two_dh // 2) * 5, "xclip_geglu_ln_bwd", dh_grad.data_ptr(), dh_grad.stride(0), u.data_ptr(),
               u.stride(0), stats.data_ptr(), g.data_ptr(), du.data_ptr(), du.stride(0), _ptr(dg),
               rows, two_dh // 2, _stream())
     return du
@@ -145,11 +192,12 @@ def l2norm_fwd(p):
     _need(p, F32, "p"); _rows2d(p, "p")
     rows, d = p.shape
     z = torch.empty((rows, d), device=p.device, dtype=F32)
-    z16 = torch.empty((rows, d), device=p.device, dtype=BF16)
+    zrow = torch.empty((rows, 3 * d), device=p.device, dtype=BF16)
+    zcol = torch.empty((rows, 3 * d), device=p.device, dtype=BF16)
     inv = torch.empty((rows,), device=p.device, dtype=F32)
-    _lib.call("xclip_l2norm_fwd", p.data_ptr(), p.stride(0), z.data_ptr(), z16.data_ptr(),
-              inv.data_ptr(), rows, d, _stream())
-    return z, z16, inv
+    _call("l2norm", 0.0, rows * d * (4 + 4 + 12), "xclip_l2norm_fwd", p.data_ptr(), p.stride(0), z.data_ptr(), zrow.data_ptr(),
+              zcol.data_ptr(), inv.data_ptr(), rows, d, _stream())
+    return z, zrow, zcol, inv
 
 
 def l2norm_bwd(dz, z, inv):
@@ -157,7 +205,7 @@ def l2norm_bwd(dz, z, inv):
     dz = dz.contiguous()
     rows, d = z.shape
     dp = torch.empty((rows, d), device=z.device, dtype=BF16)
-    _lib.call("xclip_l2norm_bwd", dz.data_ptr(), z.data_ptr(), inv.data_ptr(), dp.data_ptr(),
+    _call("l2norm", 0.0, rows * d * (4 + 4 + 2), "xclip_l2norm_bwd", dz.data_ptr(), z.data_ptr(), inv.data_ptr(), dp.data_ptr(),
               rows, d, _stream())
     return dp
 
@@ -170,7 +218,7 @@ def attn_fwd(qkv, key_mask, B, n, heads, scale):
     if key_mask is not None:
         if key_mask.dtype != torch.bool or tuple(key_mask.shape) != (B, n) or not key_mask.is_contiguous():
             raise _lib.XClipB200Error("attn_fwd: key_mask must be a contiguous bool [B, n]")
-    _lib.call("xclip_attn_fwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
+    _call("attn_fwd", 4.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 4, "xclip_attn_fwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
               o.stride(0), lse.data_ptr(), B, n, heads, float(scale), _stream())
     return o, lse
 
@@ -180,34 +228,38 @@ def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, heads, n), device=qkv.device, dtype=F32)
     ws = torch.empty((B * n, heads * 64), device=qkv.device, dtype=F32) if n > 128 else None
-    _lib.call("xclip_attn_bwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
+    _call("attn_bwd", 10.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 8, "xclip_attn_bwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
               o.stride(0), d_o.data_ptr(), d_o.stride(0), lse.data_ptr(), delta.data_ptr(),
               dqkv.data_ptr(), dqkv.stride(0), _ptr(ws), B, n, heads, float(scale), _stream())
     return dqkv
 
 
 def nce_fwd(a, b, temp_exp, diag_offset, dcl, loss_accum=None, loss_scale=0.0):
-    """Row-block InfoNCE forward: returns (lse [R], pos [R]) for rows a against all columns b."""
-    _need(a, BF16, "a"); _need(b, BF16, "b")
+    """Row-block InfoNCE forward: (lse [R], pos [R]) for rows a vs all columns b.
+    temp_exp: fp32 DEVICE scalar tensor holding exp(temperature)."""
+    _need(a, BF16, "a"); _need(b, BF16, "b"); _need(temp_exp, F32, "temp_exp")
     R, D = a.shape
     C = b.shape[0]
     nblk = _lib.load().xclip_nce_num_col_blocks(C)
     part = torch.empty((nblk, R), device=a.device, dtype=F32)
     pos = torch.empty((R,), device=a.device, dtype=F32)
     lse = torch.empty((R,), device=a.device, dtype=F32)
-    _lib.call("xclip_nce_fwd", a.data_ptr(), b.data_ptr(), R, C, D, float(temp_exp),
+    _call("nce_fwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R, "xclip_nce_fwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
               int(diag_offset), 1 if dcl else 0, part.data_ptr(), pos.data_ptr(), lse.data_ptr(),
               _ptr(loss_accum), float(loss_scale), _stream())
     return lse, pos
 
 
-def nce_bwd(a, b, temp_exp, diag_offset, dcl, lse_row, lse_col, w_row, w_col, w_diag, dtemp=None):
-    """g bf16 [R, roundup8(C)] (columns >= C are zero); see xclip_nce_bwd."""
+def nce_bwd(a, b, temp_exp, diag_offset, dcl, lse_row, lse_col, w_row, w_col, w_diag, gscale,
+            dtemp=None):
+    """bf16 temp*g [R, roundup8(C)] (columns >= C are zero); see xclip_nce_bwd."""
+    _need(gscale, F32, "gscale")
     R, D = a.shape
     C = b.shape[0]
     ldg = (C + 7) // 8 * 8
     g = torch.empty((R, ldg), device=a.device, dtype=BF16)
-    _lib.call("xclip_nce_bwd", a.data_ptr(), b.data_ptr(), R, C, D, float(temp_exp),
+    _call("nce_bwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 2.0 * R * C, "xclip_nce_bwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
               int(diag_offset), 1 if dcl else 0, _ptr(lse_row), _ptr(lse_col), float(w_row),
-              float(w_col), float(w_diag), g.data_ptr(), ldg, _ptr(dtemp), _stream())
+              float(w_col), float(w_diag), gscale.data_ptr(), g.data_ptr(), ldg, _ptr(dtemp),
+              _stream())
     return g
