@@ -100,7 +100,7 @@ int xclip_l2norm_bwd(const float* dz, const float* z, const float* inv, void* dp
 int xclip_cast_f32_bf16(const float* src, void* dst, int64_t n, xclip_stream_t stream);
 
 /* ---- fused attention (tcgen05) -------------------------------------------
- * Attention core of x_clip/x_clip.py:217-244 (dim_head = 64, n <= 384, non-causal):
+ * Attention core of x_clip/x_clip.py:217-244 (dim_head = 64, n <= 320, non-causal):
  * qkv bf16 [B*n, ld_qkv] holds q | k | v, each heads*64 wide, head-major inside.
  * key_mask uint8 [B, n] (1 = attend; may be NULL).  o bf16 [B*n, ldo] (heads merged).
  * lse f32 [B, heads, n]: base-2 log-sum-exp of scale*log2(e)*scores (saved for backward). */

@@ -16,7 +16,7 @@ def _ref_attention(qkv, mask, B, n, H, scale):
 
 
 CASES = [(2, 33, 4, False), (3, 65, 8, False), (2, 128, 2, True), (2, 17, 4, True),
-         (2, 197, 12, False), (2, 257, 8, True), (1, 384, 2, True), (5, 78, 8, True)]
+         (2, 197, 12, False), (2, 257, 8, True), (1, 320, 2, True), (5, 78, 8, True)]
 
 
 def _mk(B, n, H, masked, dev, seed=0):

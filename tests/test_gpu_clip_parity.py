@@ -3,7 +3,9 @@ produced by the reference and (b) the CPU oracle run live on the same protocol w
 
 Tolerances (bf16 MMA operands/activations, fp32 accumulation/statistics/loss; compared with the
 fp32 reference): loss rel-err <= 1e-3 (north star); latents cosine >= 0.999; d temperature within
-1e-2 relative (+1e-4 absolute: it is a difference of O(1) terms); global grad-norm rel <= 1e-2;
+1e-2 relative + 1e-3 absolute (d temperature = sum_rc g_rc*s_rc cancels O(1) terms - sum |g*s| ~
+exp(temperature) ~ 2.7 - so bf16-level perturbations of the encoders move it by ~5e-4 absolute at
+these 4-6 sample batches whatever its size; measured 2e-4..7e-4); global grad-norm rel <= 1e-2;
 per-parameter gradient cosine >= 0.99 for every tensor with a non-negligible gradient."""
 import json
 from pathlib import Path
@@ -59,7 +61,7 @@ def test_clip_matches_reference(cuda_device, case):
         assert cos >= 0.999, f"{name} latents cosine {cos}"
 
     dt = grads["temperature"].item()
-    assert abs(dt - gold["dtemperature"]) <= 1e-2 * abs(gold["dtemperature"]) + 1e-4, (dt, gold["dtemperature"])
+    assert abs(dt - gold["dtemperature"]) <= 1e-2 * abs(gold["dtemperature"]) + 1e-3, (dt, gold["dtemperature"])
     gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
     assert abs(gn - gold["grad_norm"]) <= 1e-2 * gold["grad_norm"], (gn, gold["grad_norm"])
 

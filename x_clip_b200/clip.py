@@ -151,6 +151,7 @@ class TextTransformer(nn.Module):
         super().__init__()
         _require(not rotary_pos_emb, "text_rotary_pos_emb is not implemented")
         _require(not causal, "text_causal_mask is not implemented")
+        _require(max_seq_len + 1 <= 320, "text_seq_len + CLS must be <= 320 tokens")
         self.token_emb = nn.Embedding(num_tokens, dim)
         self.abs_pos_emb = nn.Embedding(max_seq_len, dim)
         self.cls_token = nn.Parameter(torch.randn(dim))
@@ -175,6 +176,7 @@ class VisionTransformer(nn.Module):
         num_patches = (image_size // patch_size) ** 2
         patch_dim = channels * patch_size ** 2
         _require(patch_dim % 8 == 0, "channels * patch_size^2 must be a multiple of 8")
+        _require(num_patches <= 320, "at most 320 image patches are supported")
         self.to_tokens = nn.Sequential(_Slot(), nn.Linear(patch_dim, dim))
         self.pos_emb = nn.Embedding(num_patches, dim)
         self.patch_dropout = PatchDropout(patch_dropout)

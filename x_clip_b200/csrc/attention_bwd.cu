@@ -1,12 +1,12 @@
-// Fused multi-head attention backward (dim_head = 64, n <= 384), sm_100a tcgen05.
+// Fused multi-head attention backward (dim_head = 64, n <= 320), sm_100a tcgen05.
 //
 // Backward of the reference's Attention core (x_clip/x_clip.py:217-244) as produced by
 // autograd over einsum/softmax/einsum; scores are recomputed on-chip from Q,K and the saved
 // per-row log-sum-exp, never read from HBM.
 //
 // One CTA owns one (batch, head).  Outer loop over key tiles j (128 keys), inner loop over
-// query tiles i (128 queries).  Per (j,i), five tcgen05 MMAs, all fed from the natural TMA
-// boxes [128 tokens x 64] of Q, K, V, dO (K-major or MN-major descriptors pick the
+// query tiles i (128 queries).  Per (j,i) "pair", five tcgen05 MMAs, all fed from the natural
+// TMA boxes [128 tokens x 64] of Q, K, V, dO (K-major or MN-major descriptors pick the
 // orientation - nothing is transposed in memory):
 //   S   = Q_i K_j^T          (queries on TMEM lanes)        [128 x 128]
 //   dP  = dO_i V_j^T                                        [128 x 128]
@@ -16,12 +16,18 @@
 //   dQ_i  = dS   K_j         (A = dS as K-major,  B = K_j  as MN-major)   [128 x 64]
 // dK_j/dV_j accumulate in TMEM across i.  dQ_i accumulates across the (<= 3) key tiles through
 // an fp32 workspace that the same thread re-reads (same CTA, same row: no atomics, L2 resident).
+//
+// 8 compute warps (a query row is shared by two threads, 64 key columns each) + 1 control warp.
+// The control thread runs a software pipeline over the CTA's linear stream of pairs: K/V and
+// Q/dO tiles are double-buffered and prefetched by TMA, and S/dP of the next pair are issued
+// right behind the three gradient MMAs of the current one.
 #include "common.cuh"
 #include "host.h"
 
 namespace xclip {
 
-constexpr int kBwdThreads = 160;
+constexpr int kBwdComputeWarps = 8;
+constexpr int kBwdThreads = (kBwdComputeWarps + 1) * 32;
 constexpr int kBT = 128;
 constexpr int kBDh = 64;
 constexpr int kBBox = kBT * kBDh * 2;  // 16 KiB
@@ -36,6 +42,28 @@ struct AttnBwdParams {
   long long ld;
   float* dq_ws;          // fp32 [B*n, H*64] or null when n <= 128
 };
+
+__device__ __forceinline__ float bwd_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bwd_sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                           uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+               "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ float4 bwd_lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bwd_sts_f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]; one warp per (token, 4 heads at a time)
 __global__ void __launch_bounds__(256)
@@ -75,36 +103,40 @@ attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restr
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + kBBox;
-  uint8_t* sQ = sV + kBBox;
-  uint8_t* sdO = sQ + kBBox;
-  uint8_t* sP = sdO + kBBox;        // 2 blocks of [128 x 64] bf16
-  uint8_t* sdS = sP + 2 * kBBox;    // 2 blocks
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sKV = smem;                  // 2 buffers x (K box, V box)
+  uint8_t* sQdO = sKV + 4 * kBBox;      // 2 buffers x (Q box, dO box)
+  uint8_t* sP = sQdO + 4 * kBBox;       // 2 blocks of [128 x 64] bf16
+  uint8_t* sdS = sP + 2 * kBBox;        // 2 blocks
   uint8_t* tail = sdS + 2 * kBBox;
-  uint64_t* kv_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* qdo_bar = kv_bar + 1;
-  uint64_t* s_bar = kv_bar + 2;
-  uint64_t* pds_bar = kv_bar + 3;
-  uint64_t* g_bar = kv_bar + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 5);
-  uint8_t* sMask = tail + 64;  // [128] validity of the current key tile
+  uint64_t* kv_bar = reinterpret_cast<uint64_t*>(tail);  // [2]
+  uint64_t* qdo_bar = kv_bar + 2;                        // [2]
+  uint64_t* s_bar = kv_bar + 4;
+  uint64_t* pds_bar = kv_bar + 5;
+  uint64_t* g_bar = kv_bar + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 7);
+  const uint32_t sMul = smem_u32(tail + 64);   // [128] f32: scale*log2e for attendable keys, else 0
+  const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool is_control = warp == kBwdComputeWarps;
 
   if (threadIdx.x == 0) {
-    mbar_init(kv_bar, 1);
-    mbar_init(qdo_bar, 1);
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("xclip attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    mbar_init(&kv_bar[0], 1);
+    mbar_init(&kv_bar[1], 1);
+    mbar_init(&qdo_bar[0], 1);
+    mbar_init(&qdo_bar[1], 1);
     mbar_init(s_bar, 1);
-    mbar_init(pds_bar, 4);
+    mbar_init(pds_bar, kBwdComputeWarps);
     mbar_init(g_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (is_control) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
@@ -119,118 +151,180 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                  tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
   const int ntiles = (p.n + kBT - 1) / kBT;
+  const int pairs_per_bh = ntiles * ntiles;
   const int inner = p.H * kBDh;
-  uint32_t kv_phase = 0, it_phase = 0;
+  const int num_bh = p.B * p.H;
+  // this CTA's work: bh = blockIdx.x + k*gridDim.x, k = 0..my_bh-1; linear pair index pc
+  const int my_bh = (num_bh - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_pairs = my_bh * pairs_per_bh;
 
-  for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
-    const int b = bh / p.H, h = bh % p.H;
-    for (int j = 0; j < ntiles; ++j) {
-      if (warp < 4) {
-        const int key = j * kBT + threadIdx.x;
-        sMask[threadIdx.x] =
-            (key < p.n) ? (p.mask ? p.mask[(long long)b * p.n + key] : (uint8_t)1) : (uint8_t)0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      } else if (lane == 0) {
-        mbar_arrive_expect_tx(kv_bar, 2 * kBBox);
-        tma_load_3d(sK, &tm_qkv, kv_bar, inner + h * kBDh, j * kBT, b);
-        tma_load_3d(sV, &tm_qkv, kv_bar, 2 * inner + h * kBDh, j * kBT, b);
+  if (is_control) {
+    // ===================== control warp =====================
+    if (lane == 0) {
+      auto decode = [&](int pc, int& bh, int& j, int& i) {
+        const int k = pc / pairs_per_bh, r = pc % pairs_per_bh;
+        bh = blockIdx.x + k * gridDim.x;
+        j = r / ntiles;
+        i = r % ntiles;
+      };
+      auto load_kv = [&](int pc) {      // pc = first pair of a key step; kc = running key-step id
+        int bh, j, i;
+        decode(pc, bh, j, i);
+        const int kc = pc / ntiles;
+        const int b = bh / p.H, h = bh % p.H;
+        uint8_t* dst = sKV + (kc & 1) * 2 * kBBox;
+        mbar_arrive_expect_tx(&kv_bar[kc & 1], 2 * kBBox);
+        tma_load_3d(dst, &tm_qkv, &kv_bar[kc & 1], inner + h * kBDh, j * kBT, b);
+        tma_load_3d(dst + kBBox, &tm_qkv, &kv_bar[kc & 1], 2 * inner + h * kBDh, j * kBT, b);
+      };
+      auto load_qdo = [&](int pc) {
+        int bh, j, i;
+        decode(pc, bh, j, i);
+        const int b = bh / p.H, h = bh % p.H;
+        uint8_t* dst = sQdO + (pc & 1) * 2 * kBBox;
+        mbar_arrive_expect_tx(&qdo_bar[pc & 1], 2 * kBBox);
+        tma_load_3d(dst, &tm_qkv, &qdo_bar[pc & 1], h * kBDh, i * kBT, b);
+        tma_load_3d(dst + kBBox, &tm_do, &qdo_bar[pc & 1], h * kBDh, i * kBT, b);
+      };
+      auto issue_scores = [&](int pc) {  // S and dP of pair pc
+        const int kc = pc / ntiles;
+        constexpr uint32_t idesc = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);
+        const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
+        const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
+        const uint64_t qd = make_smem_desc(qd_, 0, 1024);
+        const uint64_t kd = make_smem_desc(kv, 0, 1024);
+        const uint64_t dod = make_smem_desc(qd_ + kBBox, 0, 1024);
+        const uint64_t vd = make_smem_desc(kv + kBBox, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < kBDh / 16; ++k)
+          umma_bf16(tS, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc, k > 0);
+#pragma unroll
+        for (int k = 0; k < kBDh / 16; ++k)
+          umma_bf16(tdP, desc_advance(dod, k * 32), desc_advance(vd, k * 32), idesc, k > 0);
+        umma_commit(s_bar);
+      };
+
+      if (my_pairs > 0) {
+        load_kv(0);
+        load_qdo(0);
+        mbar_wait(&kv_bar[0], 0);
+        mbar_wait(&qdo_bar[0], 0);
+        tcgen05_fence_after();
+        issue_scores(0);
       }
+      for (int pc = 0; pc < my_pairs; ++pc) {
+        const int i = pc % ntiles;
+        const int kc = pc / ntiles;
+        const bool has_next = pc + 1 < my_pairs;
+        // all MMAs of pair pc-1 retired: its Q/dO buffer and (if it closed a key step) the
+        // K/V buffer of that step may be overwritten
+        if (pc >= 1) mbar_wait(g_bar, (pc - 1) & 1);
+        if (i == 0 && (kc + 1) * ntiles < my_pairs) load_kv((kc + 1) * ntiles);  // next key step
+        if (has_next) load_qdo(pc + 1);
 
-      for (int i = 0; i < ntiles; ++i) {
-        if (warp == 4) {
-          // ===================== control warp =====================
-          if (lane == 0) {
-            mbar_arrive_expect_tx(qdo_bar, 2 * kBBox);
-            tma_load_3d(sQ, &tm_qkv, qdo_bar, h * kBDh, i * kBT, b);
-            tma_load_3d(sdO, &tm_do, qdo_bar, h * kBDh, i * kBT, b);
-            if (i == 0) mbar_wait(kv_bar, kv_phase);
-            mbar_wait(qdo_bar, it_phase);
-            tcgen05_fence_after();
-            {
-              constexpr uint32_t idesc = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);
-              const uint64_t qd = make_smem_desc(smem_u32(sQ), 0, 1024);
-              const uint64_t kd = make_smem_desc(smem_u32(sK), 0, 1024);
-              const uint64_t dod = make_smem_desc(smem_u32(sdO), 0, 1024);
-              const uint64_t vd = make_smem_desc(smem_u32(sV), 0, 1024);
+        mbar_wait(pds_bar, pc & 1);   // P, dS of pair pc are in smem; S/dP TMEM consumed
+        tcgen05_fence_after();
+        {
+          constexpr uint32_t idesc_t = make_idesc_bf16(kBT, kBDh, kMajorMN, kMajorMN);
+          constexpr uint32_t idesc_q = make_idesc_bf16(kBT, kBDh, kMajorK, kMajorMN);
+          const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
+          const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
 #pragma unroll
-              for (int k = 0; k < kBDh / 16; ++k)
-                umma_bf16(tS, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc, k > 0);
-#pragma unroll
-              for (int k = 0; k < kBDh / 16; ++k)
-                umma_bf16(tdP, desc_advance(dod, k * 32), desc_advance(vd, k * 32), idesc, k > 0);
-            }
-            umma_commit(s_bar);
-
-            mbar_wait(pds_bar, it_phase);
-            tcgen05_fence_after();
-            {
-              constexpr uint32_t idesc_t = make_idesc_bf16(kBT, kBDh, kMajorMN, kMajorMN);
-              constexpr uint32_t idesc_q = make_idesc_bf16(kBT, kBDh, kMajorK, kMajorMN);
-#pragma unroll
-              for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 queries
-                const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
-                const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
-                const uint64_t dob = make_smem_desc(smem_u32(sdO) + k * 2048, 8192, 1024);
-                const uint64_t qb = make_smem_desc(smem_u32(sQ) + k * 2048, 8192, 1024);
-                umma_bf16(tdV, pT, dob, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-                umma_bf16(tdK, dsT, qb, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-              }
-#pragma unroll
-              for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 keys
-                const uint64_t dsk =
-                    make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
-                const uint64_t kb = make_smem_desc(smem_u32(sK) + k * 2048, 8192, 1024);
-                umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
-              }
-            }
-            umma_commit(g_bar);
-            mbar_wait(g_bar, it_phase);  // smem operands + S/dP TMEM reusable
+          for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 queries
+            const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
+            const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
+            const uint64_t dob = make_smem_desc(qd_ + kBBox + k * 2048, 8192, 1024);
+            const uint64_t qb = make_smem_desc(qd_ + k * 2048, 8192, 1024);
+            umma_bf16(tdV, pT, dob, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tdK, dsT, qb, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
           }
-          __syncwarp();
-        } else {
-          // ===================== compute warps =====================
-          const int row = warp * 32 + lane;
+#pragma unroll
+          for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 keys
+            const uint64_t dsk =
+                make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
+            const uint64_t kb = make_smem_desc(kv + k * 2048, 8192, 1024);
+            umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(g_bar);
+        if (has_next) {               // S/dP of the next pair queue right behind
+          const int nkc = (pc + 1) / ntiles;
+          if ((pc + 1) % ntiles == 0) mbar_wait(&kv_bar[nkc & 1], (nkc >> 1) & 1);
+          mbar_wait(&qdo_bar[(pc + 1) & 1], ((pc + 1) >> 1) & 1);
+          tcgen05_fence_after();
+          issue_scores(pc + 1);
+        }
+      }
+      if (my_pairs > 0) mbar_wait(g_bar, (my_pairs - 1) & 1);
+    }
+    __syncwarp();
+  } else {
+    // ===================== compute warps =====================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    int pc = 0;
+    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
+      const int b = bh / p.H, h = bh % p.H;
+      for (int j = 0; j < ntiles; ++j) {
+        // key-tile tables (all compute threads are past every read of the previous tables:
+        // the last read precedes their pds arrive of the previous pair, and bar.sync orders)
+        if (threadIdx.x < kBT) {
+          const int key = j * kBT + threadIdx.x;
+          const bool keep =
+              key < p.n && (p.mask ? (p.mask[(long long)b * p.n + key] != 0) : true);
+          bwd_sts_f(sMul + threadIdx.x * 4, keep ? p.scale_log2 : 0.f);
+          bwd_sts_f(sAdd + threadIdx.x * 4, keep ? 0.f : -INFINITY);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        for (int i = 0; i < ntiles; ++i, ++pc) {
           const int q_idx = i * kBT + row;
           const bool q_ok = q_idx < p.n;
-          const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-          float lse_i = 0.f, delta_i = 0.f;
+          float lse_i = INFINITY, delta_i = 0.f;   // +inf -> p = 0 for rows beyond n
           if (q_ok) {
             const long long s_idx = ((long long)b * p.H + h) * p.n + q_idx;
             lse_i = p.lse[s_idx];
             delta_i = p.delta[s_idx];
           }
-          mbar_wait(s_bar, it_phase);
+          mbar_wait(s_bar, pc & 1);
           tcgen05_fence_after();
-#pragma unroll 1
-          for (int c0 = 0; c0 < kBT; c0 += 32) {
+#pragma unroll
+          for (int cc0 = 0; cc0 < 2; ++cc0) {
+            const int c0 = half * 64 + cc0 * 32;
             uint32_t sv[32], dv[32];
             tmem_ld_32x32(tS + lane_off + c0, sv);
             tmem_ld_32x32(tdP + lane_off + c0, dv);
             tmem_ld_wait();
             float pr[32], ds[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float pv = 0.f;
-              if (q_ok && sMask[c0 + e]) pv = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - lse_i);
-              pr[e] = pv;
-              ds[e] = pv * (__uint_as_float(dv[e]) - delta_i) * p.scale;
+            for (int e = 0; e < 32; e += 4) {
+              const float4 m = bwd_lds_f4(sMul + (c0 + e) * 4);
+              const float4 a = bwd_lds_f4(sAdd + (c0 + e) * 4);
+              const float mm[4] = {m.x, m.y, m.z, m.w}, aa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float t = fmaf(__uint_as_float(sv[e + u]), mm[u], aa[u]);
+                const float pv = bwd_ex2(t - lse_i);
+                pr[e + u] = pv;
+                ds[e + u] = pv * (__uint_as_float(dv[e + u]) - delta_i) * p.scale;
+              }
             }
-            uint8_t* pblk = sP + (c0 >> 6) * kBBox;
-            uint8_t* dblk = sdS + (c0 >> 6) * kBBox;
+            const uint32_t pblk = smem_u32(sP) + (c0 >> 6) * kBBox;
+            const uint32_t dblk = smem_u32(sdS) + (c0 >> 6) * kBBox;
             const int chunk0 = (c0 & 63) >> 3;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-              uint4 o;
-              o.x = pack_bf16x2(pr[cc * 8 + 0], pr[cc * 8 + 1]);
-              o.y = pack_bf16x2(pr[cc * 8 + 2], pr[cc * 8 + 3]);
-              o.z = pack_bf16x2(pr[cc * 8 + 4], pr[cc * 8 + 5]);
-              o.w = pack_bf16x2(pr[cc * 8 + 6], pr[cc * 8 + 7]);
-              *reinterpret_cast<uint4*>(pblk + swz128(row, chunk0 + cc)) = o;
-              o.x = pack_bf16x2(ds[cc * 8 + 0], ds[cc * 8 + 1]);
-              o.y = pack_bf16x2(ds[cc * 8 + 2], ds[cc * 8 + 3]);
-              o.z = pack_bf16x2(ds[cc * 8 + 4], ds[cc * 8 + 5]);
-              o.w = pack_bf16x2(ds[cc * 8 + 6], ds[cc * 8 + 7]);
-              *reinterpret_cast<uint4*>(dblk + swz128(row, chunk0 + cc)) = o;
+              bwd_sts_v4(pblk + swz128(row, chunk0 + cc),
+                         pack_bf16x2(pr[cc * 8 + 0], pr[cc * 8 + 1]),
+                         pack_bf16x2(pr[cc * 8 + 2], pr[cc * 8 + 3]),
+                         pack_bf16x2(pr[cc * 8 + 4], pr[cc * 8 + 5]),
+                         pack_bf16x2(pr[cc * 8 + 6], pr[cc * 8 + 7]));
+              bwd_sts_v4(dblk + swz128(row, chunk0 + cc),
+                         pack_bf16x2(ds[cc * 8 + 0], ds[cc * 8 + 1]),
+                         pack_bf16x2(ds[cc * 8 + 2], ds[cc * 8 + 3]),
+                         pack_bf16x2(ds[cc * 8 + 4], ds[cc * 8 + 5]),
+                         pack_bf16x2(ds[cc * 8 + 6], ds[cc * 8 + 7]));
             }
           }
           fence_proxy_async_smem();
@@ -238,20 +332,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_bar);
 
-          // dQ_i partial for this key tile
-          mbar_wait(g_bar, it_phase);
+          // dQ_i partial for this key tile: this thread owns 32 of the 64 columns of its row
+          mbar_wait(g_bar, pc & 1);
           tcgen05_fence_after();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          {
             uint32_t v[32];
-            tmem_ld_32x32(tdQ + lane_off + c * 32, v);
+            tmem_ld_32x32(tdQ + lane_off + half * 32, v);
             tmem_ld_wait();
             if (q_ok) {
               const long long tok = (long long)b * p.n + q_idx;
               float f[32];
 #pragma unroll
               for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-              float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + c * 32 : nullptr;
+              float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + half * 32 : nullptr;
               if (j > 0) {
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
@@ -264,7 +357,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 for (int e = 0; e < 32; e += 4)
                   *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
               } else {
-                bf16* dst = p.dqkv + tok * p.ld + h * kBDh + c * 32;
+                bf16* dst = p.dqkv + tok * p.ld + h * kBDh + half * 32;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8) {
                   uint4 o;
@@ -278,25 +371,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             }
           }
           tcgen05_fence_before();
-        }
-        it_phase ^= 1;
-      }  // i
+        }  // i
 
-      // dK_j, dV_j complete (last g_bar was waited by everyone)
-      if (warp < 4) {
-        const int row = warp * 32 + lane;
-        const int key = j * kBT + row;
-        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-        tcgen05_fence_after();
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {   // 0: dK, 1: dV
+        // dK_j (half 0) / dV_j (half 1) are complete: the last g_bar of this key step was waited
+        {
+          const int key = j * kBT + row;
+          tcgen05_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32((which == 0 ? tdK : tdV) + lane_off + c * 32, v);
+            tmem_ld_32x32((half == 0 ? tdK : tdV) + lane_off + c * 32, v);
             tmem_ld_wait();
             if (key < p.n) {
-              bf16* dst = p.dqkv + ((long long)b * p.n + key) * p.ld + (which + 1) * inner +
+              bf16* dst = p.dqkv + ((long long)b * p.n + key) * p.ld + (half + 1) * inner +
                           h * kBDh + c * 32;
 #pragma unroll
               for (int e = 0; e < 32; e += 8) {
@@ -309,17 +396,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
               }
             }
           }
+          tcgen05_fence_before();
         }
-        tcgen05_fence_before();
-      }
-      kv_phase ^= 1;
-      __syncthreads();  // K/V smem, sMask and the dK/dV accumulators are free for the next tile
-    }  // j
+      }  // j
+    }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (is_control) {
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -337,7 +422,7 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
   int rc = xclip_init();
   if (rc) return rc;
   XCLIP_REQUIRE(qkv && o && d_o && lse && delta && dqkv, "attn_bwd: null pointer");
-  XCLIP_REQUIRE(B > 0 && heads > 0 && n > 0 && n <= 384, "attn_bwd: bad sizes B=%d n=%d heads=%d",
+  XCLIP_REQUIRE(B > 0 && heads > 0 && n > 0 && n <= 320, "attn_bwd: bad sizes B=%d n=%d heads=%d",
                 B, n, heads);
   XCLIP_REQUIRE(n <= 128 || dq_workspace != nullptr,
                 "attn_bwd: n=%d > 128 needs the fp32 dq workspace [B*n, heads*64]", n);
@@ -375,7 +460,7 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
                       (uint64_t)lddo, (uint64_t)n * lddo, kBDh, kBT);
   if (rc) return rc;
 
-  const int smem = 8 * kBBox + 64 + 128 + 1024;
+  const int smem = 12 * kBBox + 64 + 2 * 128 * 4;
   static bool configured = false;
   if (!configured) {
     XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

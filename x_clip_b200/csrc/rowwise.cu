@@ -203,131 +203,131 @@ ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restric
 //   fwd: h = LN(v) * g ; stats = (mean, rstd) of v
 //   bwd: dv = LN-bwd(dh);  dval = dv * gelu(gate);  dgate = dv * val * gelu'(gate)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 output resolution):
+// one MUFU.RCP + one MUFU.EX2 + 6 FMA instead of libdevice erff's ~25 instructions.  The GEGLU
+// kernels would otherwise be instruction-bound, not HBM-bound.  exp(-x^2/2) is shared with the
+// Gaussian density that gelu'(x) needs.
+struct GeluParts {
+  float cdf;   // Phi(x) = 0.5 * (1 + erf(x / sqrt(2)))
+  float pdf;   // phi(x) = exp(-x^2/2) / sqrt(2 pi)
+};
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;            // |x| / sqrt(2)
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e_half = exp2f(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  const float erfc_z = poly * e_half * e_half;                 // exp(-z^2) = exp(-x^2/2)^2
+  const float half_erfc = 0.5f * erfc_z;
+  GeluParts g;
+  g.cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
+  g.pdf = 0.3989422804014327f * e_half;
+  return g;
 }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) +
-         x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 
-// The hidden width (4*dim) is 1024..4096, too wide for one warp's registers, so these two
-// kernels give one ROW to a 128-thread block: thread t owns 16-byte vectors t, t+128, ...
-constexpr int kWideThreads = 128;
-
-__device__ __forceinline__ float2 block_sum2(float a, float b, float* scratch /* [8] */) {
+// The hidden width DH = 4*dim is 1024..4096: one ROW per block of DH/8 threads, each thread
+// owns exactly one 16-byte vector of value, gate and gradient (low register count -> many rows
+// in flight per SM, which is what an HBM-bound kernel needs).
+template <int WARPS>
+__device__ __forceinline__ float2 block_sum2(float a, float b, float* scratch /* [2*WARPS] */) {
   a = warp_sum(a);
   b = warp_sum(b);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();  // scratch reuse across rows
-  if (lane == 0) { scratch[warp] = a; scratch[4 + warp] = b; }
+  __syncthreads();  // scratch reuse across calls
+  if (lane == 0) { scratch[warp] = a; scratch[WARPS + warp] = b; }
   __syncthreads();
-  return make_float2(scratch[0] + scratch[1] + scratch[2] + scratch[3],
-                     scratch[4] + scratch[5] + scratch[6] + scratch[7]);
+  float ra = 0.f, rb = 0.f;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) { ra += scratch[w]; rb += scratch[WARPS + w]; }
+  return make_float2(ra, rb);
 }
 
-template <int NV>  // NV = DH / 1024
-__global__ void __launch_bounds__(kWideThreads)
+template <int THREADS>  // THREADS = DH / 8
+__global__ void __launch_bounds__(THREADS)
 geglu_ln_fwd_kernel(const bf16* __restrict__ u, long long ldu, const float* __restrict__ g,
                     bf16* __restrict__ h, long long ldh, float* __restrict__ stats, int rows,
                     float eps) {
-  constexpr int DH = NV * 1024;
-  __shared__ float scratch[8];
-  const int t = threadIdx.x;
+  constexpr int DH = THREADS * 8;
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float scratch[2 * WARPS];
+  const int col = threadIdx.x * 8;
+  float gg[8];
+  loadf8(g + col, gg);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    float v[NV][8];
+    float v[8], gt[8];
+    load8(u + row * ldu + col, v);
+    load8(u + row * ldu + DH + col, gt);
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int col = (j * kWideThreads + t) * 8;
-      float gt[8];
-      load8(u + row * ldu + col, v[j]);
-      load8(u + row * ldu + DH + col, gt);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { v[j][e] *= gelu_erf(gt[e]); s += v[j][e]; }
-    }
-    const float mean = block_sum2(s, 0.f, scratch).x * (1.f / DH);
+    for (int e = 0; e < 8; ++e) { v[e] *= gelu_erf(gt[e]); s += v[e]; }
+    const float mean = block_sum2<WARPS>(s, 0.f, scratch).x * (1.f / DH);
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { const float c = v[j][e] - mean; q += c * c; }
-    const float rstd = rsqrtf(block_sum2(q, 0.f, scratch).x * (1.f / DH) + eps);
-    if (t == 0) {
+    for (int e = 0; e < 8; ++e) { const float c = v[e] - mean; q += c * c; }
+    const float rstd = rsqrtf(block_sum2<WARPS>(q, 0.f, scratch).x * (1.f / DH) + eps);
+    if (threadIdx.x == 0) {
       stats[2 * (long long)row] = mean;
       stats[2 * (long long)row + 1] = rstd;
     }
+    float o[8];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int col = (j * kWideThreads + t) * 8;
-      float gg[8], o[8];
-      loadf8(g + col, gg);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e];
-      store8(h + row * ldh + col, o);
-    }
+    for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * gg[e];
+    store8(h + row * ldh + col, o);
   }
 }
 
-template <int NV>  // NV = DH / 1024
-__global__ void __launch_bounds__(kWideThreads)
+template <int THREADS>  // THREADS = DH / 8
+__global__ void __launch_bounds__(THREADS, (768 / THREADS) > 0 ? (768 / THREADS) : 1)
 geglu_ln_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __restrict__ u,
                     long long ldu, const float* __restrict__ stats, const float* __restrict__ g,
                     bf16* __restrict__ du, long long lddu, float* __restrict__ dg, int rows) {
-  constexpr int DH = NV * 1024;
-  __shared__ float scratch[8];
-  const int t = threadIdx.x;
-  float dgacc[NV][8];
+  constexpr int DH = THREADS * 8;
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float scratch[2 * WARPS];
+  const int col = threadIdx.x * 8;
+  float gg[8], dgacc[8];
+  loadf8(g + col, gg);
 #pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dgacc[j][e] = 0.f;
+  for (int e = 0; e < 8; ++e) dgacc[e] = 0.f;
 
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
-    float va[NV][8], gt[NV][8], gd[NV][8];  // value, gate, gain*dh
+    float va[8], gt[8], gd[8], ge[8], vh[8];
+    load8(u + row * ldu + col, va);
+    load8(u + row * ldu + DH + col, gt);
+    load8(dh + row * lddh + col, gd);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int col = (j * kWideThreads + t) * 8;
-      float gg[8];
-      load8(u + row * ldu + col, va[j]);
-      load8(u + row * ldu + DH + col, gt[j]);
-      load8(dh + row * lddh + col, gd[j]);
-      loadf8(g + col, gg);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float vh = (va[j][e] * gelu_erf(gt[j][e]) - mean) * rstd;
-        dgacc[j][e] += gd[j][e] * vh;
-        gd[j][e] *= gg[e];
-        s1 += gd[j][e];
-        s2 += gd[j][e] * vh;
-      }
+    for (int e = 0; e < 8; ++e) {
+      const GeluParts gp = gelu_parts(gt[e]);
+      ge[e] = gt[e] * gp.cdf;
+      gt[e] = fmaf(gt[e], gp.pdf, gp.cdf);          // gate now holds gelu'(gate)
+      vh[e] = (va[e] * ge[e] - mean) * rstd;
+      dgacc[e] += gd[e] * vh[e];
+      gd[e] *= gg[e];
+      s1 += gd[e];
+      s2 += gd[e] * vh[e];
     }
-    const float2 ss = block_sum2(s1, s2, scratch);
+    const float2 ss = block_sum2<WARPS>(s1, s2, scratch);
     s1 = ss.x * (1.f / DH);
     s2 = ss.y * (1.f / DH);
+    float o_val[8], o_gate[8];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int col = (j * kWideThreads + t) * 8;
-      float o_val[8], o_gate[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float ge = gelu_erf(gt[j][e]);
-        const float vh = (va[j][e] * ge - mean) * rstd;
-        const float dv = rstd * (gd[j][e] - s1 - vh * s2);
-        o_val[e] = dv * ge;
-        o_gate[e] = dv * va[j][e] * gelu_erf_grad(gt[j][e]);
-      }
-      store8(du + row * lddu + col, o_val);
-      store8(du + row * lddu + DH + col, o_gate);
+    for (int e = 0; e < 8; ++e) {
+      const float dv = rstd * (gd[e] - s1 - vh[e] * s2);
+      o_val[e] = dv * ge[e];
+      o_gate[e] = dv * va[e] * gt[e];
     }
+    store8(du + row * lddu + col, o_val);
+    store8(du + row * lddu + DH + col, o_gate);
   }
   if (dg != nullptr) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(dg + (j * kWideThreads + t) * 8 + e, dgacc[j][e]);
+    for (int e = 0; e < 8; ++e) atomicAdd(dg + col + e, dgacc[e]);
   }
 }
 
@@ -430,7 +430,8 @@ static int row_grid(int rows) {
   return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
 }
 
-static int wide_grid(int rows, int per_sm) {
+static int wide_grid(int rows, int dh) {
+  const int per_sm = 2048 / (dh / 8);      // resident blocks per SM at DH/8 threads each
   const int cap = num_sms() * per_sm;
   return rows < cap ? rows : cap;
 }
@@ -442,16 +443,16 @@ using namespace xclip;
 #define LAUNCH_NV(KERNEL, NVAL, GRID, STREAM, ...) \
   case NVAL: KERNEL<NVAL><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;
 
-#define LAUNCH_WIDE(KERNEL, NVAL, GRID, STREAM, ...) \
-  case NVAL: KERNEL<NVAL><<<GRID, kWideThreads, 0, STREAM>>>(__VA_ARGS__); break;
+#define LAUNCH_WIDE(KERNEL, THREADS, GRID, STREAM, ...) \
+  case THREADS: KERNEL<THREADS><<<GRID, THREADS, 0, STREAM>>>(__VA_ARGS__); break;
 
-// feed-forward hidden widths 1024*{1,2,3,4} (= 4*dim for dim 256..1024): one block per row
+// feed-forward hidden widths 1024*{1,2,3,4} (= 4*dim for dim 256..1024): DH/8 threads per row
 #define DISPATCH_WIDE(KERNEL, D, GRID, STREAM, ...)                                       \
-  switch ((D) / 1024) {                                                                   \
-    LAUNCH_WIDE(KERNEL, 1, GRID, STREAM, __VA_ARGS__)                                     \
-    LAUNCH_WIDE(KERNEL, 2, GRID, STREAM, __VA_ARGS__)                                     \
-    LAUNCH_WIDE(KERNEL, 3, GRID, STREAM, __VA_ARGS__)                                     \
-    LAUNCH_WIDE(KERNEL, 4, GRID, STREAM, __VA_ARGS__)                                     \
+  switch ((D) / 8) {                                                                      \
+    LAUNCH_WIDE(KERNEL, 128, GRID, STREAM, __VA_ARGS__)                                   \
+    LAUNCH_WIDE(KERNEL, 256, GRID, STREAM, __VA_ARGS__)                                   \
+    LAUNCH_WIDE(KERNEL, 384, GRID, STREAM, __VA_ARGS__)                                   \
+    LAUNCH_WIDE(KERNEL, 512, GRID, STREAM, __VA_ARGS__)                                   \
     default:                                                                              \
       return fail(XCLIP_ERR_INVALID, "hidden width %d unsupported (1024*{1,2,3,4})", (D)); \
   }
@@ -520,7 +521,7 @@ extern "C" int xclip_geglu_ln_fwd(const void* u, int64_t ldu, const float* g, vo
   XCLIP_REQUIRE(ldu % 8 == 0 && ldh % 8 == 0 && ldu >= 2 * dh, "geglu_ln_fwd: bad leading dims");
   XCLIP_REQUIRE(ALIGNED16(u) && ALIGNED16(h) && ALIGNED16(g), "geglu_ln_fwd: misaligned pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_WIDE(geglu_ln_fwd_kernel, dh, wide_grid(rows, 12), s, (const bf16*)u, ldu, g, (bf16*)h, ldh,
+  DISPATCH_WIDE(geglu_ln_fwd_kernel, dh, wide_grid(rows, dh), s, (const bf16*)u, ldu, g, (bf16*)h, ldh,
                 stats, rows, eps)
   XCLIP_LAUNCH_CHECK("geglu_ln_fwd_kernel");
   return XCLIP_OK;
@@ -538,7 +539,7 @@ extern "C" int xclip_geglu_ln_bwd(const void* dh_, int64_t lddh, const void* u, 
   XCLIP_REQUIRE(ALIGNED16(dh_) && ALIGNED16(u) && ALIGNED16(du) && ALIGNED16(g),
                 "geglu_ln_bwd: misaligned pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_WIDE(geglu_ln_bwd_kernel, dh, wide_grid(rows, 4), s, (const bf16*)dh_, lddh, (const bf16*)u, ldu,
+  DISPATCH_WIDE(geglu_ln_bwd_kernel, dh, wide_grid(rows, dh), s, (const bf16*)dh_, lddh, (const bf16*)u, ldu,
                 stats, g, (bf16*)du, lddu, dg, rows)
   XCLIP_LAUNCH_CHECK("geglu_ln_bwd_kernel");
   return XCLIP_OK;
