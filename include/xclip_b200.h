@@ -137,6 +137,44 @@ int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, const float
                   float w_row, float w_col, float w_diag, const float* gscale, void* g,
                   int64_t ldg, float* dtemp, xclip_stream_t stream);
 
+/* ---- FILIP fine-grained loss (x_clip/x_clip.py:799-811 + :821-847) -----------------------
+ * segmax : a bf16 [R,D] token latents of one modality, b bf16 [C,D] token latents of the other,
+ *          C = n_samples * seg_len (seg_len tokens per sample, multiple of 16, <= 256).  For
+ *          every row r and sample y: seg_max[r,y] = max_i s, seg_arg[r,y] = argmax_i s with
+ *          s = *temp_exp * <a_r, b_(y,i)> (optionally s*col_mul[c] + col_add[c]: padded text
+ *          tokens get col_mul 0 / col_add -FLT_MAX, the reference's masked_fill at :810).
+ * reduce : out[a,b] = sum_k weights[a*len+k] * seg_max[(a*len+k), b]  ([samples, nseg] or
+ *          transposed) - the masked mean over text tokens (:807) / mean over image tokens (:811).
+ * nce_fwd/bwd : row-wise InfoNCE / DCL on a [B,B] fp32 similarity matrix (:821-847);
+ *          bwd writes g = *gscale * (softmax_row - identity).
+ * expand : rows [row0,row0+rows) of the backward operand G[R,C] (bf16): at the argmax column
+ *          of each (row, sample) the value *temp_exp * wmat[row/rows_per_sample, sample] *
+ *          rowscale[row], zero elsewhere; *dtemp += sum w * seg_max.  d rows = G @ b and
+ *          d cols += G^T @ a then run on xclip_gemm_bf16. */
+int xclip_filip_segmax(const void* a, const void* b, int R, int C, int D, const float* temp_exp,
+                       int seg_len, const float* col_mul, const float* col_add, float* seg_max,
+                       int* seg_arg, xclip_stream_t stream);
+int xclip_filip_reduce(const float* seg_max, const float* weights, int samples, int len, int nseg,
+                       float* out, int transpose_out, xclip_stream_t stream);
+int xclip_filip_nce_fwd(const float* s, int B, int dcl, float* lse, float* loss_accum,
+                        float loss_scale, xclip_stream_t stream);
+int xclip_filip_nce_bwd(const float* s, const float* lse, int B, int dcl, const float* gscale,
+                        float* g, xclip_stream_t stream);
+int xclip_filip_expand(const int* seg_arg, const float* seg_max, const float* wmat,
+                       const float* rowscale, const float* temp_exp, int row0, int rows,
+                       int rows_per_sample, int seg_len, int nseg, void* g, int64_t ldg,
+                       float* dtemp, xclip_stream_t stream);
+
+/* ---- text embedding (x_clip/x_clip.py:320-332) ---------------------------------------------
+ * fwd: out bf16 [B, n+1, d]: out[b,0] = cls, out[b,1+t] = tok[ids[b,t]] + pos[t]  (fp32 tables,
+ *      ids int64 [B,n], clamped to [0, vocab)).
+ * bwd: dx bf16 [B, n+1, d] -> dtok f32 [vocab,d] (+=, vector reductions), dpos f32 [>=n, d] (+=),
+ *      dcls f32 [d] (+=).  All three gradients must be zero-initialised by the caller. */
+int xclip_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos, const float* cls,
+                         void* out, int B, int n, int d, int vocab, xclip_stream_t stream);
+int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float* dpos, float* dcls,
+                         int B, int n, int d, int vocab, xclip_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

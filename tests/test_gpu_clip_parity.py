@@ -16,7 +16,8 @@ import torch
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
 
-TINY_CASES = ["tiny_plain", "tiny_nomask", "tiny_dcl", "tiny_extra", "tiny_dcl_extra", "tiny_patchdrop"]
+TINY_CASES = ["tiny_plain", "tiny_nomask", "tiny_dcl", "tiny_extra", "tiny_dcl_extra", "tiny_patchdrop",
+              "tiny_filip", "tiny_filip_dcl_extra"]
 
 
 def _run(case, dev):
@@ -54,11 +55,18 @@ def test_clip_matches_reference(cuda_device, case):
     rel = abs(loss - gold["loss"]) / abs(gold["loss"])
     assert rel <= 1e-3, f"loss {loss} vs reference {gold['loss']} (rel {rel:.2e})"
 
-    zt_ref = torch.tensor(gold["text_latents"])
-    zi_ref = torch.tensor(gold["image_latents"])
-    for z, ref, name in ((lat[0], zt_ref, "text"), (lat[1], zi_ref, "image")):
-        cos = torch.nn.functional.cosine_similarity(z, ref, dim=-1).min().item()
-        assert cos >= 0.999, f"{name} latents cosine {cos}"
+    if "text_latents" in gold:
+        zt_ref = torch.tensor(gold["text_latents"])
+        zi_ref = torch.tensor(gold["image_latents"])
+        for z, ref, name in ((lat[0], zt_ref, "text"), (lat[1], zi_ref, "image")):
+            cos = torch.nn.functional.cosine_similarity(z, ref, dim=-1).min().item()
+            assert cos >= 0.999, f"{name} latents cosine {cos}"
+    else:       # FILIP: token-level latents [B, T, D]; the golden file keeps checksums only
+        for z, ref in zip(lat, gold["latents"]):
+            assert list(z.shape) == ref["shape"]
+            assert abs(z.double().abs().sum().item() - ref["abs_sum"]) <= 5e-3 * ref["abs_sum"]
+            head = torch.tensor(ref["head"])
+            assert torch.allclose(z.flatten()[:8].double(), head.double(), atol=2e-2)
 
     dt = grads["temperature"].item()
     assert abs(dt - gold["dtemperature"]) <= 1e-2 * abs(gold["dtemperature"]) + 1e-3, (dt, gold["dtemperature"])
@@ -68,8 +76,8 @@ def test_clip_matches_reference(cuda_device, case):
     bad = []
     for k, g in grads.items():
         og = p[k].grad
-        if og is None or og.norm().item() < 1e-3 * gold["grad_norm"]:
-            continue
+        if k == "temperature" or og is None or og.norm().item() < 1e-3 * gold["grad_norm"]:
+            continue        # (temperature is a scalar: checked above with its own tolerance)
         cos = torch.nn.functional.cosine_similarity(g.flatten().double(), og.flatten().double(), dim=0).item()
         nrel = abs(g.norm().item() - og.norm().item()) / og.norm().item()
         if cos < 0.99 or nrel > 5e-2:
@@ -112,3 +120,23 @@ def test_state_dict_roundtrip_and_early_returns(cuda_device):
         assert sim2.shape == (4,)
     with pytest.raises(AssertionError):
         clip(text, image, return_loss=True)        # loss while .eval(), reference x_clip.py:651
+
+
+def test_weight_cache_not_confused_by_recycled_parameters(cuda_device):
+    """Two models built one after the other with different weights must not share bf16 shadows
+    (parameter ids / storage can be recycled by Python and the caching allocator)."""
+    from oracle import clip_oracle as O
+    import x_clip_b200
+    gold = json.loads((GOLD / "tiny_plain.json").read_text())
+    cfg = O.ClipConfig(**gold["cfg"])
+    text, image = O.protocol_inputs(cfg, 4, 4321, 0.1)
+    text, image = text.to(cuda_device), image.to(cuda_device)
+    losses = []
+    for seed in (1, 2, 1):
+        clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0.).to(cuda_device)
+        clip.load_state_dict(O.protocol_state_dict(cfg, seed))
+        clip.train()
+        losses.append(clip(text, image, return_loss=True).item())
+        del clip
+    assert abs(losses[0] - losses[2]) < 1e-6
+    assert abs(losses[0] - losses[1]) > 1e-4

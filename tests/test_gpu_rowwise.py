@@ -106,3 +106,26 @@ def test_cast(cuda_device):
     for n in (1, 7, 8, 1000003):
         src = torch.randn(n, device=cuda_device)
         assert torch.equal(K.cast_bf16(src), src.bfloat16())
+
+
+def test_text_embed_fwd_bwd(cuda_device):
+    """[cls | tok[ids] + pos] and its backward (x_clip/x_clip.py:320-332) vs torch autograd."""
+    from x_clip_b200 import engine as E
+    torch.manual_seed(4)
+    B, n, d, vocab = 37, 16, 512, 100
+    ids = torch.randint(0, vocab, (B, n), device=cuda_device)
+    tok = torch.randn(vocab, d, device=cuda_device, requires_grad=True)
+    pos = torch.randn(n + 4, d, device=cuda_device, requires_grad=True)
+    cls = torch.randn(d, device=cuda_device, requires_grad=True)
+    out = E.TextEmbedFn.apply(ids, tok, pos, cls)
+    ref = torch.cat((cls.expand(B, 1, d), tok[ids] + pos[:n]), dim=1)
+    assert out.shape == (B, n + 1, d)
+    _close(out, ref, 1e-2, "embed fwd")
+    dx = torch.randn(B, n + 1, d, device=cuda_device).bfloat16()
+    out.backward(dx)
+    g = (tok.grad.clone(), pos.grad.clone(), cls.grad.clone())
+    tok.grad = pos.grad = cls.grad = None
+    ref.backward(dx.float())
+    _close(g[0], tok.grad, 1e-5, "dtok")
+    _close(g[1], pos.grad, 1e-5, "dpos")
+    _close(g[2], cls.grad, 1e-5, "dcls")

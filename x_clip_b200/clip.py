@@ -159,9 +159,9 @@ class TextTransformer(nn.Module):
 
     def forward(self, x, mask=None):
         b, n = x.shape
-        tok = self.token_emb(x) + self.abs_pos_emb.weight[:n]
-        cls = self.cls_token.expand(b, 1, -1)
-        h = torch.cat((cls, tok), dim=1).to(BF16)
+        _require(x.is_cuda, "inputs must live on a CUDA (sm_100) device")
+        _require(n <= self.abs_pos_emb.num_embeddings, "text longer than text_seq_len")
+        h = E.TextEmbedFn.apply(x, self.token_emb.weight, self.abs_pos_emb.weight, self.cls_token)
         if mask is not None:
             mask = torch.cat((torch.ones(b, 1, dtype=torch.bool, device=mask.device), mask), dim=1)
         return self.transformer(h, mask=mask)
@@ -391,7 +391,7 @@ class CLIP(nn.Module):
 
         if self.use_all_token_embeds:
             from .filip import filip_loss
-            return filip_loss(self, zt, zi, zt_x, zi_x, text_mask)
+            return filip_loss(self, zt, zi, zt_x, zi_x, ops, text_mask)
 
         return E.ContrastiveLossFn.apply(
             zt, zi, zt_x if self.extra_latent_projection else None,

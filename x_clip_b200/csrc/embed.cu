@@ -1,0 +1,139 @@
+// Text token embedding + absolute position + CLS prepend (reference TextTransformer.forward,
+// x_clip/x_clip.py:320-332) fused into one HBM pass, and its backward.
+//   fwd : out[b,0,:] = cls ; out[b,1+t,:] = tok[ids[b,t],:] + pos[t,:]      fp32 tables -> bf16
+//   bwd : dtok[ids[b,t],:] += dx[b,1+t,:]   (vector fp32 reductions into the table gradient)
+//         dpos[t,:] = sum_b dx[b,1+t,:] ; dcls = sum_b dx[b,0,:]            (column sums, no atomics)
+#include "common.cuh"
+#include "host.h"
+
+namespace xclip {
+
+__global__ void __launch_bounds__(256)
+text_embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
+                      const float* __restrict__ pos, const float* __restrict__ cls,
+                      bf16* __restrict__ out, int B, int n, int d, int vocab) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = (long long)B * (n + 1);
+  for (long long r = warp; r < rows; r += nwarps) {
+    const int j = (int)(r % (n + 1));
+    const long long b = r / (n + 1);
+    const float* src = cls;
+    const float* add = nullptr;
+    if (j > 0) {
+      long long id = ids[b * n + (j - 1)];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+      src = tok + id * d;
+      add = pos + (long long)(j - 1) * d;
+    }
+    for (int c = lane * 8; c < d; c += 256) {
+      float4 a0 = *reinterpret_cast<const float4*>(src + c);
+      float4 a1 = *reinterpret_cast<const float4*>(src + c + 4);
+      if (add != nullptr) {
+        const float4 p0 = *reinterpret_cast<const float4*>(add + c);
+        const float4 p1 = *reinterpret_cast<const float4*>(add + c + 4);
+        a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+        a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(a0.x, a0.y); o.y = pack_bf16x2(a0.z, a0.w);
+      o.z = pack_bf16x2(a1.x, a1.y); o.w = pack_bf16x2(a1.z, a1.w);
+      *reinterpret_cast<uint4*>(out + r * d + c) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+text_embed_scatter_kernel(const long long* __restrict__ ids, const bf16* __restrict__ dx,
+                          float* __restrict__ dtok, int B, int n, int d, int vocab) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = (long long)B * n;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const long long b = r / n;
+    const int t = (int)(r % n);
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const bf16* src = dx + (b * (n + 1) + 1 + t) * d;
+    float* dst = dtok + id * d;
+    for (int c = lane * 8; c < d; c += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + c);
+      const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z),
+                   dd = unpack_bf16x2(u.w);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(a.x),
+                   "f"(a.y), "f"(bb.x), "f"(bb.y)
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + 4), "f"(cc.x),
+                   "f"(cc.y), "f"(dd.x), "f"(dd.y)
+                   : "memory");
+    }
+  }
+}
+
+// block (j, chunk): sums dx[b, j, chunk*512 .. +512) over a slice of b; 256 threads x 2 columns
+__global__ void __launch_bounds__(256)
+text_embed_colsum_kernel(const bf16* __restrict__ dx, float* __restrict__ dpos,
+                         float* __restrict__ dcls, int B, int n, int d, int bsplit) {
+  const int j = blockIdx.x;                 // 0..n
+  const int c = blockIdx.y * 512 + threadIdx.x * 2;
+  const int part = blockIdx.z;
+  if (c >= d) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = part; b < B; b += bsplit) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(dx + ((long long)b * (n + 1) + j) * d + c);
+    const float2 v = unpack_bf16x2(u);
+    s0 += v.x;
+    s1 += v.y;
+  }
+  float* dst = (j == 0) ? dcls + c : dpos + (long long)(j - 1) * d + c;
+  atomicAdd(dst, s0);
+  atomicAdd(dst + 1, s1);
+}
+
+}  // namespace xclip
+
+using namespace xclip;
+
+extern "C" int xclip_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos,
+                                    const float* cls, void* out, int B, int n, int d, int vocab,
+                                    xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(ids && tok && pos && cls && out, "text_embed_fwd: null pointer");
+  XCLIP_REQUIRE(B > 0 && n > 0 && d % 8 == 0 && vocab > 0, "text_embed_fwd: bad sizes");
+  const long long rows = (long long)B * (n + 1);
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  text_embed_fwd_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), tok, pos, cls, reinterpret_cast<bf16*>(out), B, n, d,
+      vocab);
+  XCLIP_LAUNCH_CHECK("text_embed_fwd_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float* dpos,
+                                    float* dcls, int B, int n, int d, int vocab,
+                                    xclip_stream_t stream) {
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(ids && dx && dtok && dpos && dcls, "text_embed_bwd: null pointer");
+  XCLIP_REQUIRE(B > 0 && n > 0 && d % 8 == 0 && vocab > 0, "text_embed_bwd: bad sizes");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)B * n;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  text_embed_scatter_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const long long*>(ids),
+                                                        reinterpret_cast<const bf16*>(dx), dtok, B,
+                                                        n, d, vocab);
+  XCLIP_LAUNCH_CHECK("text_embed_scatter_kernel");
+  int bsplit = (num_sms() * 4) / ((n + 1) * ((d + 511) / 512));
+  if (bsplit < 1) bsplit = 1;
+  if (bsplit > B) bsplit = B;
+  dim3 grid(n + 1, (d + 511) / 512, bsplit);
+  text_embed_colsum_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(dx), dpos, dcls, B, n,
+                                                d, bsplit);
+  XCLIP_LAUNCH_CHECK("text_embed_colsum_kernel");
+  return XCLIP_OK;
+}

@@ -46,11 +46,20 @@ struct GemmParams {
   float* dtemp;          // BWD: scalar accumulator of sum(g * s) or null
   const float* alpha_dev;  // NCE: exp(temperature) read from device memory (no host sync)
   const float* gscale_dev; // BWD: upstream scalar gradient / (2*B_global), multiplies the weights
+  // ---- FILIP segment-max epilogue (EPI_SEGMAX): columns are grouped in segments of seg_len
+  // tokens (one segment = one sample of the other modality); n_tile_stride = columns a tile
+  // advances by (a whole number of segments, <= BLOCK_N)
+  int seg_len, n_tile_stride, n_segs;
+  const float* col_mul;    // [N] or null: per-column multiplier (0 for masked text tokens)
+  const float* col_add;    // [N] or null: per-column addend (-FLT_MAX for masked text tokens)
+  float* seg_max;          // [M, n_segs]  max_i s
+  int* seg_arg;            // [M, n_segs]  argmax (index inside the segment)
 };
 
 constexpr int EPI_STORE = 0;    // C = alpha*acc (+bias) (+residual)
 constexpr int EPI_NCE_FWD = 1;  // row partial sums of exp(s - alpha) and the positives
 constexpr int EPI_NCE_BWD = 2;  // C = g = w_row*exp(s-lse_row) + w_col*exp(s-lse_col) - w_diag*[diag]
+constexpr int EPI_SEGMAX = 3;   // per row and column segment: max and argmax of alpha*acc (FILIP)
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
@@ -91,7 +100,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   const int num_m = (p.M + kGemmBlockM - 1) / kGemmBlockM;
-  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int n_stride = (EPI == EPI_SEGMAX) ? p.n_tile_stride : BLOCK_N;
+  const int num_n = (p.N + n_stride - 1) / n_stride;
   const int num_kb = (p.K + kGemmBlockK - 1) / kGemmBlockK;
   const int splits = p.split_k > 0 ? p.split_k : 1;
   const int kb_per_split = (num_kb + splits - 1) / splits;
@@ -143,12 +153,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                           m_blk * kGemmBlockM + g * 64, kb * kGemmBlockK);
           }
           if (B_MAJOR == kMajorK) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBlockK, n_blk * BLOCK_N);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBlockK, n_blk * n_stride);
           } else {
 #pragma unroll
             for (int g = 0; g < BLOCK_N / 64; ++g)
               tma_load_2d(sb + g * (kGemmBlockK * 128), &tmB, &full_bar[stage],
-                          n_blk * BLOCK_N + g * 64, kb * kGemmBlockK);
+                          n_blk * n_stride + g * 64, kb * kGemmBlockK);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -308,6 +318,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (row_ok) p.nce_part[(long long)n_blk * p.M + row] = rsum;
+      } else if constexpr (EPI == EPI_SEGMAX) {
+        const float alpha = __ldg(p.alpha_dev);
+        const int col_base = n_blk * n_stride;
+        const int valid = min(n_stride, p.N - col_base);        // multiple of seg_len (and of 16)
+        float best = -INFINITY;
+        int best_i = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < valid; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + c0, v);
+          tmem_ld_wait();
+          const int in_seg = c0 % p.seg_len;
+          if (in_seg == 0) { best = -INFINITY; best_i = 0; }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float sv = __uint_as_float(v[i]) * alpha;
+            if (p.col_mul != nullptr)
+              sv = fmaf(__uint_as_float(v[i]) * alpha, p.col_mul[col_base + c0 + i],
+                        p.col_add[col_base + c0 + i]);
+            if (sv > best) { best = sv; best_i = in_seg + i; }
+          }
+          if (in_seg + 16 == p.seg_len && row_ok) {
+            const long long o = (long long)row * p.n_segs + (col_base + c0) / p.seg_len;
+            p.seg_max[o] = best;
+            p.seg_arg[o] = best_i;
+          }
+        }
       } else {
         const float alpha = __ldg(p.alpha_dev);
         const float gs = __ldg(p.gscale_dev);

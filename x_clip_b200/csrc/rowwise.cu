@@ -213,14 +213,16 @@ struct GeluParts {
 };
 __device__ __forceinline__ GeluParts gelu_parts(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;            // |x| / sqrt(2)
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e_half = exp2f(-0.72134752044448170f * x * x);  // exp(-x^2/2)
-  const float erfc_z = poly * e_half * e_half;                 // exp(-z^2) = exp(-x^2/2)^2
+  float e_half;                                                // exp(-x^2/2) == exp(-z^2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_half) : "f"(-0.72134752044448170f * x * x));
+  const float erfc_z = poly * e_half;
   const float half_erfc = 0.5f * erfc_z;
   GeluParts g;
   g.cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
@@ -261,14 +263,14 @@ geglu_ln_fwd_kernel(const bf16* __restrict__ u, long long ldu, const float* __re
     float v[8], gt[8];
     load8(u + row * ldu + col, v);
     load8(u + row * ldu + DH + col, gt);
-    float s = 0.f;
+    float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { v[e] *= gelu_erf(gt[e]); s += v[e]; }
-    const float mean = block_sum2<WARPS>(s, 0.f, scratch).x * (1.f / DH);
-    float q = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { const float c = v[e] - mean; q += c * c; }
-    const float rstd = rsqrtf(block_sum2<WARPS>(q, 0.f, scratch).x * (1.f / DH) + eps);
+    for (int e = 0; e < 8; ++e) { v[e] *= gelu_erf(gt[e]); s += v[e]; q += v[e] * v[e]; }
+    // one block reduction for both moments: var = E[v^2] - mean^2 (|mean| << std for GEGLU
+    // outputs, so the fp32 cancellation error is ~1e-7 relative)
+    const float2 mom = block_sum2<WARPS>(s, q, scratch);
+    const float mean = mom.x * (1.f / DH);
+    const float rstd = rsqrtf(fmaxf(mom.y * (1.f / DH) - mean * mean, 0.f) + eps);
     if (threadIdx.x == 0) {
       stats[2 * (long long)row] = mean;
       stats[2 * (long long)row + 1] = rstd;

@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -28,14 +30,19 @@ _bf16_cache = {}
 
 
 def weight_bf16(p: torch.Tensor) -> torch.Tensor:
-    """bf16 copy of an fp32 parameter, cached until the parameter is modified in place."""
+    """bf16 copy of an fp32 parameter, cached until the parameter is modified in place.
+
+    The entry is validated by a weak reference to the parameter object itself (ids and data
+    pointers are recycled once a model is freed), its version counter and its storage address."""
     key = id(p)
-    ver = p._version
     hit = _bf16_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[1] == p.data_ptr():
-        return hit[2]
+    if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2] == p.data_ptr():
+        return hit[3]
     w = K.cast_bf16(p.detach())
-    _bf16_cache[key] = (ver, p.data_ptr(), w)
+    if len(_bf16_cache) > 4096:          # drop entries of models that no longer exist
+        for k in [k for k, v in _bf16_cache.items() if v[0]() is None]:
+            del _bf16_cache[k]
+    _bf16_cache[key] = (weakref.ref(p), p._version, p.data_ptr(), w)
     return w
 
 
@@ -152,6 +159,26 @@ class TransformerFn(torch.autograd.Function):
         grads[0] = dg_in
         ctx.saved = None
         return (dx_in.view(B, n, d), None, None, None, *grads)
+
+
+class TextEmbedFn(torch.autograd.Function):
+    """[cls | token_emb[ids] + abs_pos_emb] -> bf16 [B, n+1, d] (x_clip.py:320-332), one pass."""
+
+    @staticmethod
+    def forward(ctx, ids, tok, pos, cls):
+        out = K.text_embed_fwd(ids, tok.detach(), pos.detach(), cls.detach())
+        ctx.save_for_backward(ids)
+        ctx.shapes = (tok.shape[0], pos.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ids,) = ctx.saved_tensors
+        vocab, pos_rows = ctx.shapes
+        if dx.dtype != BF16:
+            dx = dx.to(BF16)
+        dtok, dpos, dcls = K.text_embed_bwd(ids, dx, vocab, pos_rows)
+        return None, dtok, dpos, dcls
 
 
 class LinearFn(torch.autograd.Function):

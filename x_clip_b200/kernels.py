@@ -263,3 +263,76 @@ def nce_bwd(a, b, temp_exp, diag_offset, dcl, lse_row, lse_col, w_row, w_col, w_
               float(w_col), float(w_diag), gscale.data_ptr(), g.data_ptr(), ldg, _ptr(dtemp),
               _stream())
     return g
+
+
+def filip_segmax(a, b, temp_exp, seg_len, col_mul, col_add):
+    """Per row of a and per seg_len-long block of rows of b: max / argmax of temp * <a_r, b_c>."""
+    _need(a, BF16, "a"); _need(b, BF16, "b")
+    R, D = a.shape
+    C = b.shape[0]
+    nseg = C // seg_len
+    seg_max = torch.empty((R, nseg), device=a.device, dtype=F32)
+    seg_arg = torch.empty((R, nseg), device=a.device, dtype=torch.int32)
+    _call("filip_segmax", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R * nseg, "xclip_filip_segmax",
+          a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(), int(seg_len), _ptr(col_mul),
+          _ptr(col_add), seg_max.data_ptr(), seg_arg.data_ptr(), _stream())
+    return seg_max, seg_arg
+
+
+def filip_reduce(seg_max, weights, samples, length, nseg, transpose):
+    out = torch.empty((nseg, samples) if transpose else (samples, nseg), device=seg_max.device, dtype=F32)
+    _call("filip_small", 0.0, 4.0 * seg_max.numel(), "xclip_filip_reduce", seg_max.data_ptr(),
+          weights.data_ptr(), samples, length, nseg, out.data_ptr(), 1 if transpose else 0, _stream())
+    return out
+
+
+def filip_nce_fwd(s, dcl, loss_accum, loss_scale):
+    B = s.shape[0]
+    lse = torch.empty((B,), device=s.device, dtype=F32)
+    _call("filip_small", 0.0, 4.0 * s.numel(), "xclip_filip_nce_fwd", s.data_ptr(), B,
+          1 if dcl else 0, lse.data_ptr(), _ptr(loss_accum), float(loss_scale), _stream())
+    return lse
+
+
+def filip_nce_bwd(s, lse, dcl, gscale):
+    B = s.shape[0]
+    g = torch.empty_like(s)
+    _call("filip_small", 0.0, 8.0 * s.numel(), "xclip_filip_nce_bwd", s.data_ptr(), lse.data_ptr(), B,
+          1 if dcl else 0, gscale.data_ptr(), g.data_ptr(), _stream())
+    return g
+
+
+def filip_expand(seg_arg, seg_max, wmat, rowscale, temp_exp, row0, rows, rows_per_sample, seg_len,
+                 nseg, dtemp):
+    g = torch.empty((rows, nseg * seg_len), device=seg_arg.device, dtype=BF16)
+    _call("filip_expand", 0.0, 2.0 * g.numel(), "xclip_filip_expand", seg_arg.data_ptr(),
+          seg_max.data_ptr(), wmat.data_ptr(), rowscale.data_ptr(), temp_exp.data_ptr(), int(row0),
+          int(rows), int(rows_per_sample), int(seg_len), int(nseg), g.data_ptr(), g.stride(0),
+          _ptr(dtemp), _stream())
+    return g
+
+
+def text_embed_fwd(ids, tok, pos, cls):
+    """ids int64 [B,n] -> bf16 [B, n+1, d] = [cls | tok[ids] + pos]."""
+    if ids.dtype != torch.int64 or not ids.is_cuda:
+        raise _lib.XClipB200Error("text_embed: ids must be a CUDA int64 tensor")
+    ids = ids.contiguous()
+    B, n = ids.shape
+    vocab, d = tok.shape
+    out = torch.empty((B, n + 1, d), device=ids.device, dtype=BF16)
+    _call("embed", 0.0, B * (n + 1) * d * 6.0, "xclip_text_embed_fwd", ids.data_ptr(), tok.data_ptr(),
+          pos.data_ptr(), cls.data_ptr(), out.data_ptr(), B, n, d, vocab, _stream())
+    return out
+
+
+def text_embed_bwd(ids, dx, vocab, pos_rows):
+    ids = ids.contiguous()
+    B, n = ids.shape
+    d = dx.shape[-1]
+    dx = dx.contiguous()
+    dtok = torch.zeros((vocab, d), device=dx.device, dtype=F32)
+    dpos = torch.zeros((pos_rows, d), device=dx.device, dtype=F32)
+    dcls = torch.zeros((d,), device=dx.device, dtype=F32)
+    _call("embed", 0.0, B * (n + 1) * d * 8.0, "xclip_text_embed_bwd", ids.data_ptr(), dx.data_ptr(),
+          dtok.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, n, d, vocab, _stream())
+    return dtok, dpos, dcls
