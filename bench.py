@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU")
     ap.add_argument("--patch-dropout", type=float, default=0.5)
+    ap.add_argument("--microbatch", type=int, default=0,
+                    help="encoder micro-batch (GradCache-style step) - lets --batch 4096 fit one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -187,7 +189,8 @@ def main():
 
     B = args.batch
     torch.manual_seed(0)
-    clip = x_clip_b200.CLIP(**README_CFG, visual_patch_dropout=args.patch_dropout).to(dev)
+    clip = x_clip_b200.CLIP(**README_CFG, visual_patch_dropout=args.patch_dropout,
+                            microbatch=args.microbatch or None).to(dev)
     clip.train()
     params = [p for p in clip.parameters()]
 
@@ -334,7 +337,9 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(b=B), "global_batch": Bg, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD.format(b=B) + (f", encoder micro-batch {args.microbatch} "
+                   "(two-pass GradCache step: +1 encoder forward)" if args.microbatch else ""),
+                   "global_batch": Bg, "parallelism": f"dp{world}",
                    "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed",
                    "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks",
                    "loss": round(last_loss, 5)},

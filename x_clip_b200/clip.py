@@ -257,6 +257,7 @@ class CLIP(nn.Module):
         multiview_loss_weight=0.1,
         checkpoint_during_training=False,
         sim_reg_loss_weight=0.,
+        microbatch=None,   # (extension) encoder micro-batch for the GradCache-style large-batch step
         **kwargs,     # unknown keywords are swallowed, like the reference (:455)
     ):
         super().__init__()
@@ -319,12 +320,30 @@ class CLIP(nn.Module):
         self.to_visual_latent_extra = copy.deepcopy(self.to_visual_latent)
 
         self.multiview_loss_weight = multiview_loss_weight
+        self.microbatch = microbatch
         # latched at construction, like the reference (:591): the process group must exist first
         self.requires_all_gather = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.sim_reg_loss_weight = sim_reg_loss_weight
         self.has_sim_reg_loss = False
 
     # -- helpers ---------------------------------------------------------------------
+    def _encode_to_latents(self, text, image, text_mask):
+        """encoders -> CLS select -> projections (CLS mode).  Returns ([zt, zi(, zt_x, zi_x)], ops)."""
+        text_args = (text,) if self.text_encode_without_mask else (text, text_mask)
+        enc_text = self.text_transformer(*text_args)
+        enc_image = self.visual_transformer(image)
+        te = enc_text[:, 0] if enc_text.ndim == 3 else enc_text
+        ie = enc_image[:, 0] if enc_image.ndim == 3 else enc_image
+        zt, ops_t = self._project(te, self.to_text_latent)
+        zi, ops_i = self._project(ie, self.to_visual_latent)
+        zs, ops = [zt, zi], [ops_t, ops_i]
+        if self.extra_latent_projection:
+            zt_x, ops_tx = self._project(te, self.to_text_latent_extra)
+            zi_x, ops_ix = self._project(ie, self.to_visual_latent_extra)
+            zs += [zt_x, zi_x]
+            ops += [ops_tx, ops_ix]
+        return zs, ops
+
     def _project(self, embeds: torch.Tensor, linear: nn.Linear):
         """embeds [..., d] (any float dtype) -> (z fp32 [..., D], (zrow, zcol) bf16 [rows, 3D])."""
         lead = embeds.shape[:-1]
@@ -352,6 +371,10 @@ class CLIP(nn.Module):
         _require(text.is_cuda and image.is_cuda, "inputs must live on a CUDA (sm_100) device")
 
         text_mask = text != self.text_pad_id
+        if (return_loss and self.microbatch and text.shape[0] > self.microbatch
+                and not self.use_all_token_embeds and not (freeze_image_encoder or freeze_text_encoder)):
+            return E.ChunkedClipLossFn.apply(self, text, image, text_mask, int(self.microbatch),
+                                             self.temperature)
         text_args = (text,) if self.text_encode_without_mask else (text, text_mask)
         enc_text = _encode(self.text_transformer, text_args, freeze_text_encoder)
         enc_image = _encode(self.visual_transformer, (image,), freeze_image_encoder)

@@ -134,6 +134,7 @@ extern "C" int xclip_filip_segmax(const void* a, const void* b, int R, int C, in
   if (rc) return rc;
   GemmParams p = {};
   p.M = R; p.N = C; p.K = D; p.split_k = 1;
+  p.raster_m_fast = (R <= C) ? 1 : 0;
   p.alpha_dev = temp_exp;
   p.seg_len = seg_len;
   p.n_tile_stride = (256 / seg_len) * seg_len;

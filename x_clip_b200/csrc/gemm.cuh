@@ -35,6 +35,8 @@ struct GemmParams {
   const bf16* residual;  // bf16 [*, N] or null
   long long ldr;
   int res_row_mod;     // residual row = row % res_row_mod when > 0 (positional tables)
+  int raster_m_fast;   // tile order: 0 = N fastest (big A streamed once, B tile L2 resident),
+                       //             1 = M fastest (small A resident, big B streamed once)
   // ---- InfoNCE / DCL epilogues (EPI_NCE_FWD, EPI_NCE_BWD); logits s = alpha * acc, alpha = exp(temperature)
   int diag_offset;       // positive of local row r sits in column r + diag_offset
   int dcl;               // decoupled contrastive learning: drop the positive from the denominators
@@ -134,8 +136,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_blk = t % num_n;
-        const int m_blk = (t / num_n) % num_m;
+        const int tmn = t % (num_n * num_m);
+        const int n_blk = p.raster_m_fast ? tmn / num_m : tmn % num_n;
+        const int m_blk = p.raster_m_fast ? tmn % num_m : tmn / num_n;
         const int split = t / (num_n * num_m);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, num_kb);
@@ -210,8 +213,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue (warps 0-3) =====================
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int n_blk = t % num_n;
-      const int m_blk = (t / num_n) % num_m;
+      const int tmn = t % (num_n * num_m);
+      const int n_blk = p.raster_m_fast ? tmn / num_m : tmn % num_n;
+      const int m_blk = p.raster_m_fast ? tmn % num_m : tmn / num_n;
       const int split = t / (num_n * num_m);
       const int kb0 = split * kb_per_split;
       const bool has_k = kb0 < min(kb0 + kb_per_split, num_kb);

@@ -73,6 +73,7 @@ static int nce_common(const void* a, const void* b, int R, int C, int D, GemmPar
   GemmParams z = {};
   *p = z;
   p->M = R; p->N = C; p->K = D; p->split_k = 1;
+  p->raster_m_fast = 1;   // latents of the local rows stay in L2, all columns stream once
   const long long tiles =
       (long long)((R + kGemmBlockM - 1) / kGemmBlockM) * ((C + *block_n - 1) / *block_n);
   *grid = (int)(tiles < num_sms() ? tiles : num_sms());

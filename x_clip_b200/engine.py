@@ -315,3 +315,61 @@ def _pad_rows(m: torch.Tensor, rows: int) -> torch.Tensor:
     out = torch.zeros((rows, m.shape[1]), device=m.device, dtype=m.dtype)
     out[: m.shape[0]] = m
     return out
+
+
+class ChunkedClipLossFn(torch.autograd.Function):
+    """Full-batch contrastive loss with micro-batched encoders (memory: one chunk of activations).
+
+    The reference offers `checkpoint_during_training` (x_clip.py:280-286) to fit large batches;
+    here the same need (4096 pairs per GPU for a 32768 global batch) is met by a GradCache-style
+    schedule that is mathematically identical to the single-pass step:
+      1. encode every chunk without saving activations -> latents of the whole local batch
+      2. one contrastive loss over ALL latents (with the usual cross-rank all-gather)
+      3. in backward: d loss / d latents, then re-encode chunk by chunk with activations saved
+         and back-propagate the matching slice of the latent gradient into the parameters.
+    RNG (PatchDropout) is replayed per chunk.  Costs one extra encoder forward (4/3 x flops)."""
+
+    @staticmethod
+    def forward(ctx, clip, text, image, text_mask, chunk, temperature):
+        B = text.shape[0]
+        bounds = [(s, min(s + chunk, B)) for s in range(0, B, chunk)]
+        rng_states, zs, opss = [], [], []
+        with torch.no_grad():
+            for s, e in bounds:
+                rng_states.append(torch.cuda.get_rng_state(text.device))
+                z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                zs.append(z)
+                opss.append(ops)
+        nsets = len(zs[0])
+        leaves = [torch.cat([z[j] for z in zs]).detach().requires_grad_(True) for j in range(nsets)]
+        ops_all = tuple((torch.cat([o[j][0] for o in opss]), torch.cat([o[j][1] for o in opss]))
+                        for j in range(nsets))
+        temp_leaf = temperature.detach().requires_grad_(True)
+        with torch.enable_grad():
+            loss = ContrastiveLossFn.apply(
+                leaves[0], leaves[1], leaves[2] if nsets == 4 else None,
+                leaves[3] if nsets == 4 else None, temp_leaf, ops_all,
+                clip.decoupled_contrastive_learning, clip.requires_all_gather)
+        ctx.clip, ctx.inputs = clip, (text, image, text_mask)
+        ctx.bounds, ctx.rng_states = bounds, rng_states
+        ctx.graph = (loss, leaves, temp_leaf)
+        return loss.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        clip = ctx.clip
+        text, image, text_mask = ctx.inputs
+        loss, leaves, temp_leaf = ctx.graph
+        with torch.enable_grad():
+            torch.autograd.backward(loss, g)
+        dz = [l.grad for l in leaves]
+        dev = text.device
+        keep_state = torch.cuda.get_rng_state(dev)
+        for (s, e), st in zip(ctx.bounds, ctx.rng_states):
+            torch.cuda.set_rng_state(st, dev)
+            with torch.enable_grad():
+                z, _ = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                torch.autograd.backward(list(z), [d[s:e] for d in dz])   # accumulates into .grad
+        torch.cuda.set_rng_state(keep_state, dev)
+        ctx.graph = ctx.inputs = None
+        return None, None, None, None, None, temp_leaf.grad
