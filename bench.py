@@ -281,10 +281,12 @@ def main():
 
     # ---- (3) instrumented step for the roofline (rank 0 only, after the timed regions)
     prof = None
-    if rank == 0 and not args.no_profile:
-        kernels.PROF.start()
+    if not args.no_profile:        # every rank runs the step (it contains collectives); rank 0 records
+        if rank == 0:
+            kernels.PROF.start()
         step(dev_text, dev_img)
-        prof = kernels.PROF.stop()
+        if rank == 0:
+            prof = kernels.PROF.stop()
     barrier()
 
     if world > 1:

@@ -151,7 +151,7 @@ extern "C" int xclip_filip_segmax(const void* a, const void* b, int R, int C, in
     XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, S::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, S::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmA, p);
   XCLIP_LAUNCH_CHECK("gemm_bf16_kernel<segmax>");
   return XCLIP_OK;
 }

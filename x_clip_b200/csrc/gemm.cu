@@ -5,8 +5,8 @@
 namespace xclip {
 
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                       int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const GemmParams& p, int grid, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MAJOR, B_MAJOR>;
   static bool configured = false;
@@ -14,21 +14,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmC, p);
   XCLIP_LAUNCH_CHECK("gemm_bf16_kernel");
   return XCLIP_OK;
 }
 
 template <int BLOCK_N>
 static int dispatch_major(int a_major, int b_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                          const GemmParams& p, int grid, cudaStream_t stream) {
+                          const CUtensorMap& tmC, const GemmParams& p, int grid,
+                          cudaStream_t stream) {
   if (a_major == kMajorK && b_major == kMajorK)
-    return launch_gemm<BLOCK_N, kMajorK, kMajorK>(tmA, tmB, p, grid, stream);
+    return launch_gemm<BLOCK_N, kMajorK, kMajorK>(tmA, tmB, tmC, p, grid, stream);
   if (a_major == kMajorK && b_major == kMajorMN)
-    return launch_gemm<BLOCK_N, kMajorK, kMajorMN>(tmA, tmB, p, grid, stream);
+    return launch_gemm<BLOCK_N, kMajorK, kMajorMN>(tmA, tmB, tmC, p, grid, stream);
   if (a_major == kMajorMN && b_major == kMajorK)
-    return launch_gemm<BLOCK_N, kMajorMN, kMajorK>(tmA, tmB, p, grid, stream);
-  return launch_gemm<BLOCK_N, kMajorMN, kMajorMN>(tmA, tmB, p, grid, stream);
+    return launch_gemm<BLOCK_N, kMajorMN, kMajorK>(tmA, tmB, tmC, p, grid, stream);
+  return launch_gemm<BLOCK_N, kMajorMN, kMajorMN>(tmA, tmB, tmC, p, grid, stream);
 }
 
 }  // namespace xclip
@@ -103,7 +104,13 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
   p.split_k = splits; p.alpha = alpha; p.bias = bias;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.res_row_mod = res_row_mod;
 
+  CUtensorMap tmC = tmA;   // placeholder unless the TMA-store epilogue is used
+  if (c_dtype == 0) {
+    rc = encode_2d_bf16(&tmC, c, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 64, kGemmBlockM);
+    if (rc) return rc;
+    p.use_tma_store = 1;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return dispatch_major<256>(a_major, b_major, tmA, tmB, p, grid, s);
-  return dispatch_major<128>(a_major, b_major, tmA, tmB, p, grid, s);
+  if (block_n == 256) return dispatch_major<256>(a_major, b_major, tmA, tmB, tmC, p, grid, s);
+  return dispatch_major<128>(a_major, b_major, tmA, tmB, tmC, p, grid, s);
 }

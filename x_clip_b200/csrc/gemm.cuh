@@ -35,6 +35,7 @@ struct GemmParams {
   const bf16* residual;  // bf16 [*, N] or null
   long long ldr;
   int res_row_mod;     // residual row = row % res_row_mod when > 0 (positional tables)
+  int use_tma_store;   // bf16 C written through swizzled smem staging + cp.async.bulk.tensor stores
   int raster_m_fast;   // tile order: 0 = N fastest (big A streamed once, B tile L2 resident),
                        //             1 = M fastest (small A resident, big B streamed once)
   // ---- InfoNCE / DCL epilogues (EPI_NCE_FWD, EPI_NCE_BWD); logits s = alpha * acc, alpha = exp(temperature)
@@ -74,24 +75,24 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + align slack
+  static constexpr int kStagingBytes = 2 * 128 * 128;  // two [128 rows x 64 bf16] output boxes
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
 };
 
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator
   static_assert(kTmemCols == 256 || kTmemCols == 512, "BLOCK_N must be 128 or 256");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* smem_c = smem + kStages * S::kStageBytes;     // epilogue staging (TMA store source)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + S::kStagingBytes);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]
@@ -110,6 +111,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = num_m * num_n * splits;
 
   if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("xclip gemm: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -123,6 +128,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.use_tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
   tcgen05_fence_before();
@@ -212,6 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue (warps 0-3) =====================
     int it = 0;
+    uint32_t store_count = 0;   // staging-buffer parity of the TMA-store path
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tmn = t % (num_n * num_m);
       const int n_blk = p.raster_m_fast ? tmn / num_m : tmn % num_n;
@@ -234,6 +241,72 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         res_row = p.residual + rr * p.ldr;
       }
       if constexpr (EPI == EPI_STORE) {
+        if (p.use_tma_store) {
+          // bf16 output: 64-column boxes staged in swizzled smem (double buffered), written by
+          // cp.async.bulk.tensor stores (full-line writes, no LSU pressure, tails clipped by TMA)
+          const int row_in_tile = warp * 32 + lane;
+#pragma unroll 1
+          for (int q = 0; q < BLOCK_N / 64; ++q) {
+            const uint32_t stg = smem_u32(smem_c) + (store_count & 1) * 16384;
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int c32 = 0; c32 < 2; ++c32) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + q * 64 + c32 * 32, v);
+              tmem_ld_wait();
+              const int col0 = n_blk * BLOCK_N + q * 64 + c32 * 32;
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (col0 + i < p.N) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+                    f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                  }
+                }
+              }
+              if (res_row != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  if (col0 + i < p.N) {
+                    const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
+                    float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
+                    float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+                    f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
+                    f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                 stg + swz128(row_in_tile, c32 * 4 + i)),
+                             "r"(pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1])),
+                             "r"(pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3])),
+                             "r"(pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5])),
+                             "r"(pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]))
+                             : "memory");
+              }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
+              const int c0 = n_blk * BLOCK_N + q * 64;
+              if (c0 < p.N) {
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                        reinterpret_cast<uint64_t>(&tmC)),
+                    "r"(stg), "r"(c0), "r"(m_blk * kGemmBlockM)
+                    : "memory");
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++store_count;
+          }
+        } else {
   #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
@@ -299,6 +372,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+        }
         }
       } else if constexpr (EPI == EPI_NCE_FWD) {
         // s = alpha*acc with |s| <= alpha (unit-norm latents): exp(s - alpha) cannot overflow.
@@ -405,6 +479,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (EPI == EPI_STORE && p.use_tma_store && threadIdx.x == 0)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();

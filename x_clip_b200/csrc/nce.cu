@@ -52,7 +52,7 @@ static int launch_nce(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmA, p);
   XCLIP_LAUNCH_CHECK("gemm_bf16_kernel<nce>");
   return XCLIP_OK;
 }
