@@ -62,7 +62,9 @@ def cpu_reference_rate(batch: int, steps: int, warmup: int, budget_s: float):
     on all host cores, README model, `batch` pairs per step, default patch dropout 0.5."""
     import torch
     from oracle import clip_oracle as O
-    cores = os.cpu_count() or 1
+    # all host threads up to 32: beyond that torch's intra-op parallelism degrades on these small
+    # per-step shapes (measured on the 128-thread GPU host: 49 s/step with 128 threads)
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     cfg = O.ClipConfig(**README_CFG)
     state = O.protocol_state_dict(cfg, 1234)

@@ -114,9 +114,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint64_t* s_bar = kv_bar + 4;
   uint64_t* pds_bar = kv_bar + 5;
   uint64_t* g_bar = kv_bar + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 7);
-  const uint32_t sMul = smem_u32(tail + 64);   // [128] f32: scale*log2e for attendable keys, else 0
+  uint64_t* dq_bar = kv_bar + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 8);
+  const uint32_t sMul = smem_u32(tail + 128);  // [128] f32: scale*log2e for attendable keys, else 0
   const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
+  const uint32_t sLse = sAdd + 128 * 4;        // [384] f32: log-sum-exp of every query of this (b,h)
+  const uint32_t sDelta = sLse + 384 * 4;      // [384] f32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,6 +137,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(s_bar, 1);
     mbar_init(pds_bar, kBwdComputeWarps);
     mbar_init(g_bar, 1);
+    mbar_init(dq_bar, 1);
     fence_barrier_init();
   }
   if (is_control) {
@@ -230,6 +234,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
           const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
 #pragma unroll
+          for (int k = 0; k < kBT / 16; ++k) {  // dQ first (contraction over the 128 keys): its
+            const uint64_t dsk =                // epilogue then overlaps the dV/dK MMAs below
+                make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
+            const uint64_t kb = make_smem_desc(kv + k * 2048, 8192, 1024);
+            umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
+          }
+          umma_commit(dq_bar);
+#pragma unroll
           for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 queries
             const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
             const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
@@ -237,13 +249,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const uint64_t qb = make_smem_desc(qd_ + k * 2048, 8192, 1024);
             umma_bf16(tdV, pT, dob, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
             umma_bf16(tdK, dsT, qb, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-          }
-#pragma unroll
-          for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 keys
-            const uint64_t dsk =
-                make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
-            const uint64_t kb = make_smem_desc(kv + k * 2048, 8192, 1024);
-            umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
           }
         }
         umma_commit(g_bar);
@@ -276,19 +281,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           bwd_sts_f(sMul + threadIdx.x * 4, keep ? p.scale_log2 : 0.f);
           bwd_sts_f(sAdd + threadIdx.x * 4, keep ? 0.f : -INFINITY);
         }
+        if (j == 0) {   // per-(b,h) row statistics: +inf lse -> p = 0 for rows beyond n
+          for (int q = threadIdx.x; q < 384; q += kBwdComputeWarps * 32) {
+            const long long s_idx = ((long long)b * p.H + h) * p.n + q;
+            bwd_sts_f(sLse + q * 4, q < p.n ? p.lse[s_idx] : INFINITY);
+            bwd_sts_f(sDelta + q * 4, q < p.n ? p.delta[s_idx] : 0.f);
+          }
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
         for (int i = 0; i < ntiles; ++i, ++pc) {
           const int q_idx = i * kBT + row;
           const bool q_ok = q_idx < p.n;
-          float lse_i = INFINITY, delta_i = 0.f;   // +inf -> p = 0 for rows beyond n
-          if (q_ok) {
-            const long long s_idx = ((long long)b * p.H + h) * p.n + q_idx;
-            lse_i = p.lse[s_idx];
-            delta_i = p.delta[s_idx];
-          }
+          float lse_i, delta_i;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lse_i) : "r"(sLse + q_idx * 4));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(delta_i) : "r"(sDelta + q_idx * 4));
           mbar_wait(s_bar, pc & 1);
           tcgen05_fence_after();
+          // P/dS smem of the previous pair is still read by its dV/dK MMAs until g_bar fires
+          if (pc >= 1) mbar_wait(g_bar, (pc - 1) & 1);
 #pragma unroll
           for (int cc0 = 0; cc0 < 2; ++cc0) {
             const int c0 = half * 64 + cc0 * 32;
@@ -332,24 +343,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_bar);
 
-          // dQ_i partial for this key tile: this thread owns 32 of the 64 columns of its row
-          mbar_wait(g_bar, pc & 1);
+          // dQ_i partial for this key tile: this thread owns 32 of the 64 columns of its row.
+          // The fp32 partial of the previous key tiles is fetched BEFORE waiting for the MMAs.
+          const long long tok = (long long)b * p.n + (q_ok ? q_idx : 0);
+          float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + half * 32 : nullptr;
+          float4 prev[8];
+          if (j > 0 && q_ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) prev[e] = *reinterpret_cast<const float4*>(ws + e * 4);
+          }
+          mbar_wait(dq_bar, pc & 1);
           tcgen05_fence_after();
           {
             uint32_t v[32];
             tmem_ld_32x32(tdQ + lane_off + half * 32, v);
             tmem_ld_wait();
             if (q_ok) {
-              const long long tok = (long long)b * p.n + q_idx;
               float f[32];
 #pragma unroll
               for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-              float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + half * 32 : nullptr;
               if (j > 0) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                  const float4 a = *reinterpret_cast<const float4*>(ws + e);
-                  f[e] += a.x; f[e + 1] += a.y; f[e + 2] += a.z; f[e + 3] += a.w;
+                for (int e = 0; e < 8; ++e) {
+                  f[e * 4] += prev[e].x; f[e * 4 + 1] += prev[e].y;
+                  f[e * 4 + 2] += prev[e].z; f[e * 4 + 3] += prev[e].w;
                 }
               }
               if (j < ntiles - 1) {
@@ -373,9 +390,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           tcgen05_fence_before();
         }  // i
 
-        // dK_j (half 0) / dV_j (half 1) are complete: the last g_bar of this key step was waited
+        // dK_j (half 0) / dV_j (half 1) are complete once the last pair's dV/dK MMAs retired
         {
           const int key = j * kBT + row;
+          mbar_wait(g_bar, (pc - 1) & 1);
           tcgen05_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -460,7 +478,7 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
                       (uint64_t)lddo, (uint64_t)n * lddo, kBDh, kBT);
   if (rc) return rc;
 
-  const int smem = 12 * kBBox + 64 + 2 * 128 * 4;
+  const int smem = 12 * kBBox + 128 + 2 * 128 * 4 + 2 * 384 * 4;
   static bool configured = false;
   if (!configured) {
     XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
