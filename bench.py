@@ -35,9 +35,18 @@ sys.path.insert(0, str(ROOT))
 README_CFG = dict(dim_text=512, dim_image=512, dim_latent=512, num_text_tokens=10000,
                   text_enc_depth=6, text_seq_len=256, text_heads=8, visual_enc_depth=6,
                   visual_image_size=256, visual_patch_size=32, visual_heads=8)
+# cfg3 of BASELINE.json: ViT-B/16 image tower + 12-layer text tower (CLIP tokenizer vocabulary)
+VITB16_CFG = dict(dim_text=512, dim_image=768, dim_latent=512, num_text_tokens=49408,
+                  text_enc_depth=12, text_seq_len=77, text_heads=8, visual_enc_depth=12,
+                  visual_image_size=224, visual_patch_size=16, visual_heads=12)
 METRIC = "image-text pairs/sec (fwd+bwd)"
-WORKLOAD = ("cfg2: README CLIP (dim 512, text 6L seq 256, ViT 6L 256px/32, 8 heads, "
-            "visual_patch_dropout 0.5 (reference default), plain InfoNCE), {b} pairs/GPU")
+WORKLOADS = {
+    "cfg2": (README_CFG, "cfg2: README CLIP (dim 512, text 6L seq 256, ViT 6L 256px/32, 8 heads, "
+                         "visual_patch_dropout {pd} (reference default 0.5), plain InfoNCE), {b} pairs/GPU"),
+    "cfg3": (VITB16_CFG, "cfg3: ViT-B/16 (dim 768, 12L, 12 heads, 224px/16) + text 12L dim 512 seq 77, "
+                         "dim_latent 512, visual_patch_dropout {pd}, plain InfoNCE, {b} pairs/GPU"),
+}
+WORKLOAD = WORKLOADS["cfg2"][1]
 
 
 def parse():
@@ -48,6 +57,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU")
     ap.add_argument("--patch-dropout", type=float, default=0.5)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--microbatch", type=int, default=0,
                     help="encoder micro-batch (GradCache-style step) - lets --batch 4096 fit one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -101,7 +111,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(b=args.batch), "sample_batch": batch,
+        "config": {"workload": WORKLOAD.format(b=args.batch, pd=0.5), "sample_batch": batch,
                    "note": "CPU arm: oracle port of the reference (pure-PyTorch fp32), all host threads"},
         "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": sample},
@@ -191,7 +201,8 @@ def main():
 
     B = args.batch
     torch.manual_seed(0)
-    clip = x_clip_b200.CLIP(**README_CFG, visual_patch_dropout=args.patch_dropout,
+    model_cfg, workload_txt = WORKLOADS[args.workload]
+    clip = x_clip_b200.CLIP(**model_cfg, visual_patch_dropout=args.patch_dropout,
                             microbatch=args.microbatch or None).to(dev)
     clip.train()
     params = [p for p in clip.parameters()]
@@ -200,8 +211,10 @@ def main():
     g = torch.Generator().manual_seed(1 + rank)
     host = []
     for _ in range(2):
-        t = torch.randint(0, 10000, (B, 256), generator=g).pin_memory()
-        im = torch.randn(B, 3, 256, 256, generator=g).pin_memory()
+        t = torch.randint(0, model_cfg["num_text_tokens"], (B, model_cfg["text_seq_len"]),
+                          generator=g).pin_memory()
+        im = torch.randn(B, 3, model_cfg["visual_image_size"], model_cfg["visual_image_size"],
+                         generator=g).pin_memory()
         host.append((t, im))
     dev_text = host[0][0].to(dev)
     dev_img = host[0][1].to(dev)
@@ -329,7 +342,7 @@ def main():
                     "share_of_step": round(g_ms / total_ms, 4)}
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2":
         rate, ms, cores, n = cpu_reference_rate(4, steps=30, warmup=2, budget_s=20.0)
         cpu_baseline = {"value": round(rate, 3), "unit": "pairs/s", "cores": cores, "kind": "port",
                         "sample": f"{n} steps of cfg1 (README model, batch 4, fp32, fwd+bwd) on the "
@@ -341,7 +354,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(b=B) + (f", encoder micro-batch {args.microbatch} "
+        "config": {"workload": workload_txt.format(b=B, pd=args.patch_dropout) + (f", encoder micro-batch {args.microbatch} "
                    "(two-pass GradCache step: +1 encoder forward)" if args.microbatch else ""),
                    "global_batch": Bg, "parallelism": f"dp{world}",
                    "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed",

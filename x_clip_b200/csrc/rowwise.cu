@@ -24,6 +24,12 @@ __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+         d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -259,10 +265,23 @@ geglu_ln_fwd_kernel(const bf16* __restrict__ u, long long ldu, const float* __re
   const int col = threadIdx.x * 8;
   float gg[8];
   loadf8(g + col, gg);
+  // software pipeline: the next row's vectors are in flight while this row is reduced
+  // (block-level syncs otherwise limit the bytes in flight per SM and the kernel becomes
+  // latency- instead of HBM-bound)
+  uint4 nv = make_uint4(0, 0, 0, 0), ng = nv;
+  if (blockIdx.x < rows) {
+    nv = *reinterpret_cast<const uint4*>(u + (long long)blockIdx.x * ldu + col);
+    ng = *reinterpret_cast<const uint4*>(u + (long long)blockIdx.x * ldu + DH + col);
+  }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     float v[8], gt[8];
-    load8(u + row * ldu + col, v);
-    load8(u + row * ldu + DH + col, gt);
+    unpack8(nv, v);
+    unpack8(ng, gt);
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) {
+      nv = *reinterpret_cast<const uint4*>(u + (long long)nrow * ldu + col);
+      ng = *reinterpret_cast<const uint4*>(u + (long long)nrow * ldu + DH + col);
+    }
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { v[e] *= gelu_erf(gt[e]); s += v[e]; q += v[e] * v[e]; }
@@ -296,12 +315,24 @@ geglu_ln_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __r
 #pragma unroll
   for (int e = 0; e < 8; ++e) dgacc[e] = 0.f;
 
+  uint4 nv = make_uint4(0, 0, 0, 0), ng = nv, nd = nv;   // next row's vectors (prefetched)
+  if (blockIdx.x < rows) {
+    nv = *reinterpret_cast<const uint4*>(u + (long long)blockIdx.x * ldu + col);
+    ng = *reinterpret_cast<const uint4*>(u + (long long)blockIdx.x * ldu + DH + col);
+    nd = *reinterpret_cast<const uint4*>(dh + (long long)blockIdx.x * lddh + col);
+  }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
     float va[8], gt[8], gd[8], ge[8], vh[8];
-    load8(u + row * ldu + col, va);
-    load8(u + row * ldu + DH + col, gt);
-    load8(dh + row * lddh + col, gd);
+    unpack8(nv, va);
+    unpack8(ng, gt);
+    unpack8(nd, gd);
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) {
+      nv = *reinterpret_cast<const uint4*>(u + (long long)nrow * ldu + col);
+      ng = *reinterpret_cast<const uint4*>(u + (long long)nrow * ldu + DH + col);
+      nd = *reinterpret_cast<const uint4*>(dh + (long long)nrow * lddh + col);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
