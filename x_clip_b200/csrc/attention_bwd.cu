@@ -192,7 +192,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       };
       auto issue_scores = [&](int pc) {  // S and dP of pair pc
         const int kc = pc / ntiles;
-        constexpr uint32_t idesc = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);
+        const int jj = (pc % pairs_per_bh) / ntiles;
+        // only the key columns that exist (rounded to 32) are produced for a partial key tile
+        const int vc = min(kBT, (p.n - jj * kBT + 31) / 32 * 32);
+        const uint32_t idesc = make_idesc_bf16(kBT, vc, kMajorK, kMajorK);
         const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
         const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
         const uint64_t qd = make_smem_desc(qd_, 0, 1024);
@@ -219,6 +222,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int pc = 0; pc < my_pairs; ++pc) {
         const int i = pc % ntiles;
         const int kc = pc / ntiles;
+        const int j = (pc % pairs_per_bh) / ntiles;
+        const int ksteps_q = min(kBT, (p.n - i * kBT + 15) / 16 * 16) / 16;   // valid query groups
+        const int ksteps_k = min(kBT, (p.n - j * kBT + 31) / 32 * 32) / 16;   // valid key groups
         const bool has_next = pc + 1 < my_pairs;
         // all MMAs of pair pc-1 retired: its Q/dO buffer and (if it closed a key step) the
         // K/V buffer of that step may be overwritten
@@ -233,16 +239,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           constexpr uint32_t idesc_q = make_idesc_bf16(kBT, kBDh, kMajorK, kMajorMN);
           const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
           const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
-#pragma unroll
-          for (int k = 0; k < kBT / 16; ++k) {  // dQ first (contraction over the 128 keys): its
+          for (int k = 0; k < ksteps_k; ++k) {  // dQ first (contraction over the valid keys): its
             const uint64_t dsk =                // epilogue then overlaps the dV/dK MMAs below
                 make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
             const uint64_t kb = make_smem_desc(kv + k * 2048, 8192, 1024);
             umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
           }
           umma_commit(dq_bar);
-#pragma unroll
-          for (int k = 0; k < kBT / 16; ++k) {  // contraction over the 128 queries
+          for (int k = 0; k < ksteps_q; ++k) {  // contraction over the valid queries
             const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
             const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
             const uint64_t dob = make_smem_desc(qd_ + kBBox + k * 2048, 8192, 1024);
@@ -300,9 +304,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           tcgen05_fence_after();
           // P/dS smem of the previous pair is still read by its dV/dK MMAs until g_bar fires
           if (pc >= 1) mbar_wait(g_bar, (pc - 1) & 1);
+          // Partial tiles: the MMAs only touch query groups < vr16 and key columns < vc32 (see the
+          // control warp), and every output row depends on its own operand row only, so warps /
+          // chunks that are pure padding skip their math and leave their smem slots untouched.
+          const int vr16 = min(kBT, (p.n - i * kBT + 15) / 16 * 16);
+          const int vc32 = min(kBT, (p.n - j * kBT + 31) / 32 * 32);
+          const bool warp_alive = quarter * 32 < vr16;
 #pragma unroll
           for (int cc0 = 0; cc0 < 2; ++cc0) {
             const int c0 = half * 64 + cc0 * 32;
+            if (!warp_alive || c0 >= vc32) continue;
             uint32_t sv[32], dv[32];
             tmem_ld_32x32(tS + lane_off + c0, sv);
             tmem_ld_32x32(tdP + lane_off + c0, dv);

@@ -248,9 +248,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
         mbar_wait(s_bar, tc & 1);
         tcgen05_fence_after();
 
+        // a warp whose 32 query rows are all beyond n has nothing to compute: O rows depend only
+        // on their own P rows, so its smem/TMEM slots may hold anything (it still takes part in
+        // every barrier)
+        const bool warp_alive = qt * kTile + quarter * 32 < p.n;
         // pass 1: maximum of this thread's half of the row (base-2, scaled + masked scores)
         float m2 = -INFINITY;
-        for (int c = c_begin; c < c_end; ++c) {
+        for (int c = warp_alive ? c_begin : c_end; c < c_end; ++c) {
           const int c0 = c * 32;
           uint32_t v[32];
           float t[32];
@@ -277,7 +281,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
 
         // pass 2: probabilities -> bf16 P in smem (SW128 K-major blocks of 64 keys), row sum
         float sum = 0.f;
-        for (int c = c_begin; c < c_end; ++c) {
+        for (int c = warp_alive ? c_begin : c_end; c < c_end; ++c) {
           const int c0 = c * 32;
           uint32_t v[32];
           float t[32];
