@@ -62,6 +62,8 @@ def parse():
                     help="encoder micro-batch (GradCache-style step) - lets --batch 4096 fit one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="skip the host->device end-to-end leg (large per-GPU batches: no pinned staging)")
     return ap.parse_args()
 
 
@@ -210,15 +212,23 @@ def main():
     # synthetic host batches in pinned memory (two alternating buffers) + device-resident copy
     g = torch.Generator().manual_seed(1 + rank)
     host = []
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         t = torch.randint(0, model_cfg["num_text_tokens"], (B, model_cfg["text_seq_len"]),
                           generator=g).pin_memory()
         im = torch.randn(B, 3, model_cfg["visual_image_size"], model_cfg["visual_image_size"],
                          generator=g).pin_memory()
         host.append((t, im))
-    dev_text = host[0][0].to(dev)
-    dev_img = host[0][1].to(dev)
-    h2d_bytes = host[0][0].numel() * 8 + host[0][1].numel() * 4
+    if args.no_e2e:
+        gd = torch.Generator(device=dev).manual_seed(1 + rank)
+        dev_text = torch.randint(0, model_cfg["num_text_tokens"], (B, model_cfg["text_seq_len"]),
+                                 generator=gd, device=dev)
+        dev_img = torch.randn(B, 3, model_cfg["visual_image_size"], model_cfg["visual_image_size"],
+                              generator=gd, device=dev)
+        h2d_bytes = 0
+    else:
+        dev_text = host[0][0].to(dev)
+        dev_img = host[0][1].to(dev)
+        h2d_bytes = host[0][0].numel() * 8 + host[0][1].numel() * 4
 
     def step(text, image):
         for p in params:
@@ -263,8 +273,9 @@ def main():
 
     # ---- (2) end-to-end timing: pinned host -> device copy of every step's batch (side stream,
     #          double-buffered) + loss read-back, all inside the timed region
+    ms_e2e = None
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [(torch.empty_like(dev_text), torch.empty_like(dev_img)) for _ in range(2)]
+    slots = [] if args.no_e2e else [(torch.empty_like(dev_text), torch.empty_like(dev_img)) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -276,23 +287,24 @@ def main():
             slots[s][1].copy_(host[s][1], non_blocking=True)
             ready[s].record(copy_stream)
 
-    for s in range(2):
-        consumed[s].record(torch.cuda.current_stream())
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    issue_copy(0)
-    for i in range(args.steps):
-        s = i % 2
-        if i + 1 < args.steps:
-            issue_copy(i + 1)
-        torch.cuda.current_stream().wait_event(ready[s])
-        loss = step(slots[s][0], slots[s][1])
-        consumed[s].record(torch.cuda.current_stream())
-        _ = loss.item()                      # device -> host read of the step's result
-    f1.record()
-    barrier()
-    ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+    if not args.no_e2e:
+        for s in range(2):
+            consumed[s].record(torch.cuda.current_stream())
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        issue_copy(0)
+        for i in range(args.steps):
+            s = i % 2
+            if i + 1 < args.steps:
+                issue_copy(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s])
+            loss = step(slots[s][0], slots[s][1])
+            consumed[s].record(torch.cuda.current_stream())
+            _ = loss.item()                      # device -> host read of the step's result
+        f1.record()
+        barrier()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
 
     # ---- (3) instrumented step for the roofline (rank 0 only, after the timed regions)
     prof = None
@@ -361,9 +373,10 @@ def main():
                    "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks",
                    "loss": round(last_loss, 5)},
         "clocks": clocks,
-        "e2e": {"value": round(Bg * args.steps / (ms_e2e / 1e3), 2), "unit": "pairs/s",
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "e2e": None if ms_e2e is None else {
+            "value": round(Bg * args.steps / (ms_e2e / 1e3), 2), "unit": "pairs/s",
+            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+            "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
