@@ -196,6 +196,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
+    t_start = time.time()
+
+    def note(msg):
+        if os.environ.get("XCLIP_BENCH_VERBOSE"):
+            print(f"[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     import x_clip_b200
     from x_clip_b200 import _lib, kernels
     lib = _lib.load()
@@ -249,10 +255,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    note("model + data ready")
     # ---- warm-up
-    for _ in range(max(args.warmup, 1)):
+    for i in range(max(args.warmup, 1)):
         step(dev_text, dev_img)
+        note(f"warm-up step {i} enqueued")
     barrier()
+    note("warm-up done")
 
     # ---- (1) device-resident timing
     sampler = ClockSampler(local)
@@ -267,6 +276,7 @@ def main():
     e1.record()
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    note(f"device-resident timing done: {ms_dev / args.steps:.1f} ms/step")
     launches = lib.xclip_launch_count()
     last_loss = loss.item()
     clocks = sampler.stop() if rank == 0 else None
@@ -306,6 +316,7 @@ def main():
         barrier()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
 
+    note("e2e timing done")
     # ---- (3) instrumented step for the roofline (rank 0 only, after the timed regions)
     prof = None
     if not args.no_profile:        # every rank runs the step (it contains collectives); rank 0 records
@@ -316,6 +327,7 @@ def main():
             prof = kernels.PROF.stop()
     barrier()
 
+    note("profile step done")
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -341,16 +353,22 @@ def main():
         g_fl = sum(d["flops"] for d in gem)
         g_calls = sum(d["calls"] for d in gem)
         achieved = g_fl / g_ms / 1e9      # TFLOP/s
+        # DRAM traffic per launch: algorithmic bytes of the average launch (counted live) times
+        # the traffic/algorithmic ratio measured by `ncu --set full` on representative launches
+        # (profiles/r1_ncu_summary.md); null when no capture is committed
         traffic = None
         tf = ROOT / "profiles" / "gemm_traffic.json"
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+            ratio = json.loads(tf.read_text()).get("traffic_over_algorithmic")
+            if ratio:
+                traffic = round(ratio * sum(d["bytes"] for d in gem) / g_calls)
         roofline = {"kernel": "gemm_bf16_kernel (tcgen05, fwd+dgrad+wgrad launches)",
                     "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic,
                     "peak_source": peak_src, "launches_per_step": g_calls,
                     "avg_launch_ms": round(g_ms / g_calls, 4),
                     "flops_per_launch": g_fl / g_calls,
+                    "algorithmic_bytes_per_launch": round(sum(d["bytes"] for d in gem) / g_calls),
                     "share_of_step": round(g_ms / total_ms, 4)}
 
     cpu_baseline = None
