@@ -114,8 +114,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint64_t* s_bar = kv_bar + 4;
   uint64_t* pds_bar = kv_bar + 5;
   uint64_t* g_bar = kv_bar + 6;
-  uint64_t* dq_bar = kv_bar + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 8);
+  uint64_t* dq_bar = kv_bar + 7;                         // [2]: one per dQ accumulator buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 9);
   const uint32_t sMul = smem_u32(tail + 128);  // [128] f32: scale*log2e for attendable keys, else 0
   const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
   const uint32_t sLse = sAdd + 128 * 4;        // [384] f32: log-sum-exp of every query of this (b,h)
@@ -137,7 +137,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(s_bar, 1);
     mbar_init(pds_bar, kBwdComputeWarps);
     mbar_init(g_bar, 1);
-    mbar_init(dq_bar, 1);
+    mbar_init(&dq_bar[0], 1);
+    mbar_init(&dq_bar[1], 1);
     fence_barrier_init();
   }
   if (is_control) {
@@ -152,7 +153,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256,
-                 tdK = tmem_base + 320, tdQ = tmem_base + 384;
+                 tdK = tmem_base + 320, tdQ = tmem_base + 384;   // tdQ: two 64-column buffers
 
   const int ntiles = (p.n + kBT - 1) / kBT;
   const int pairs_per_bh = ntiles * ntiles;
@@ -243,9 +244,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const uint64_t dsk =                // epilogue then overlaps the dV/dK MMAs below
                 make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
             const uint64_t kb = make_smem_desc(kv + k * 2048, 8192, 1024);
-            umma_bf16(tdQ, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
+            umma_bf16(tdQ + (pc & 1) * kBDh, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
           }
-          umma_commit(dq_bar);
+          umma_commit(&dq_bar[pc & 1]);
           for (int k = 0; k < ksteps_q; ++k) {  // contraction over the valid queries
             const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
             const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
@@ -272,6 +273,57 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    // dQ_i partial of one (key tile, query tile) pair: this thread owns 32 of the 64 columns of
+    // its row; partials of earlier key tiles are re-read from the fp32 workspace first.
+    auto dq_epilogue = [&](int eb, int eh, int ei, int ej, int epc) {
+      const int q_idx = ei * kBT + row;
+      const bool q_ok = q_idx < p.n;
+          const long long tok = (long long)eb * p.n + (q_ok ? q_idx : 0);
+          float* ws = p.dq_ws ? p.dq_ws + tok * inner + eh * kBDh + half * 32 : nullptr;
+          float4 prev[8];
+          if (ej > 0 && q_ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) prev[e] = *reinterpret_cast<const float4*>(ws + e * 4);
+          }
+          mbar_wait(&dq_bar[epc & 1], (epc >> 1) & 1);
+          tcgen05_fence_after();
+          {
+            uint32_t v[32];
+            tmem_ld_32x32(tdQ + (epc & 1) * kBDh + lane_off + half * 32, v);
+            tmem_ld_wait();
+            if (q_ok) {
+              float f[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+              if (ej > 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e * 4] += prev[e].x; f[e * 4 + 1] += prev[e].y;
+                  f[e * 4 + 2] += prev[e].z; f[e * 4 + 3] += prev[e].w;
+                }
+              }
+              if (ej < ntiles - 1) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                  *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+              } else {
+                bf16* dst = p.dqkv + tok * p.ld + eh * kBDh + half * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                  uint4 o;
+                  o.x = pack_bf16x2(f[e], f[e + 1]);
+                  o.y = pack_bf16x2(f[e + 2], f[e + 3]);
+                  o.z = pack_bf16x2(f[e + 4], f[e + 5]);
+                  o.w = pack_bf16x2(f[e + 6], f[e + 7]);
+                  *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+              }
+            }
+          }
+      tcgen05_fence_before();
+    };
+    bool pend_valid = false;
+    int pend_b = 0, pend_h = 0, pend_i = 0, pend_j = 0, pend_pc = 0;
     int pc = 0;
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
       const int b = bh / p.H, h = bh % p.H;
@@ -354,50 +406,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_bar);
 
-          // dQ_i partial for this key tile: this thread owns 32 of the 64 columns of its row.
-          // The fp32 partial of the previous key tiles is fetched BEFORE waiting for the MMAs.
-          const long long tok = (long long)b * p.n + (q_ok ? q_idx : 0);
-          float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + half * 32 : nullptr;
-          float4 prev[8];
-          if (j > 0 && q_ok) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) prev[e] = *reinterpret_cast<const float4*>(ws + e * 4);
-          }
-          mbar_wait(dq_bar, pc & 1);
-          tcgen05_fence_after();
-          {
-            uint32_t v[32];
-            tmem_ld_32x32(tdQ + lane_off + half * 32, v);
-            tmem_ld_wait();
-            if (q_ok) {
-              float f[32];
-#pragma unroll
-              for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-              if (j > 0) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  f[e * 4] += prev[e].x; f[e * 4 + 1] += prev[e].y;
-                  f[e * 4 + 2] += prev[e].z; f[e * 4 + 3] += prev[e].w;
-                }
-              }
-              if (j < ntiles - 1) {
-#pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                  *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-              } else {
-                bf16* dst = p.dqkv + tok * p.ld + h * kBDh + half * 32;
-#pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                  uint4 o;
-                  o.x = pack_bf16x2(f[e], f[e + 1]);
-                  o.y = pack_bf16x2(f[e + 2], f[e + 3]);
-                  o.z = pack_bf16x2(f[e + 4], f[e + 5]);
-                  o.w = pack_bf16x2(f[e + 6], f[e + 7]);
-                  *reinterpret_cast<uint4*>(dst + e) = o;
-                }
-              }
-            }
-          }
+          // The dQ epilogue of the PREVIOUS pair runs here, after this pair's P/dS were handed
+          // to the tensor core: its MMAs (and the fp32 partial it re-reads) have had a whole
+          // compute phase to complete, so nothing on this path waits any more.
+          if (pend_valid) dq_epilogue(pend_b, pend_h, pend_i, pend_j, pend_pc);
+          pend_valid = true; pend_b = b; pend_h = h; pend_i = i; pend_j = j; pend_pc = pc;
           tcgen05_fence_before();
         }  // i
 
@@ -429,6 +442,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }  // j
     }
+    if (pend_valid) dq_epilogue(pend_b, pend_h, pend_i, pend_j, pend_pc);
   }
 
   tcgen05_fence_before();

@@ -169,16 +169,38 @@ ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restric
 #pragma unroll
   for (int j = 0; j < NV; ++j) loadf8(g + (j * 32 + lane) * 8, gg[j]);
 
+  // software pipeline: x, dy (and the residual gradient) of the warp's NEXT row are in flight
+  // while the current row is reduced
+  constexpr bool kPipelined = NV <= 2;   // wider rows would spill: they load just in time
+  uint4 nx[NV], nd[NV], na[NV];
+  float nmean = 0.f, nrstd = 0.f;
+  auto prefetch = [&](int r) {
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int col = (j * 32 + lane) * 8;
+        nx[j] = *reinterpret_cast<const uint4*>(x + r * ldx + col);
+        nd[j] = *reinterpret_cast<const uint4*>(dy + r * lddy + col);
+        if (kPipelined && add != nullptr)
+          na[j] = *reinterpret_cast<const uint4*>(add + r * ldadd + col);
+      }
+      nmean = stats[2 * (long long)r];
+      nrstd = stats[2 * (long long)r + 1];
+    }
+  };
+  if (kPipelined) prefetch(warp_global);
   for (int row = warp_global; row < rows; row += warp_stride) {
-    const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
+    if (!kPipelined) prefetch(row);
+    const float mean = nmean, rstd = nrstd;
     float xh[NV][8], gd[NV][8];
+    uint4 ca[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int col = (j * 32 + lane) * 8;
       float d8[8];
-      load8(x + row * ldx + col, xh[j]);
-      load8(dy + row * lddy + col, d8);
+      unpack8(nx[j], xh[j]);
+      unpack8(nd[j], d8);
+      if (kPipelined) ca[j] = na[j];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         xh[j][e] = (xh[j][e] - mean) * rstd;
@@ -188,13 +210,17 @@ ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restric
         s2 += gd[j][e] * xh[j][e];
       }
     }
+    if (kPipelined) prefetch(row + warp_stride);
     s1 = warp_sum(s1) * (1.f / D);
     s2 = warp_sum(s2) * (1.f / D);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int col = (j * 32 + lane) * 8;
       float a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (add != nullptr) load8(add + row * ldadd + col, a8);
+      if (add != nullptr) {
+        if (kPipelined) unpack8(ca[j], a8);
+        else load8(add + row * ldadd + col, a8);
+      }
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = rstd * (gd[j][e] - s1 - xh[j][e] * s2) + a8[e];
