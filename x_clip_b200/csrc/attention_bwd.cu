@@ -114,8 +114,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint64_t* s_bar = kv_bar + 4;
   uint64_t* pds_bar = kv_bar + 5;
   uint64_t* g_bar = kv_bar + 6;
-  uint64_t* dq_bar = kv_bar + 7;                         // [2]: one per dQ accumulator buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 9);
+  uint64_t* dq_bar = kv_bar + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 8);
   const uint32_t sMul = smem_u32(tail + 128);  // [128] f32: scale*log2e for attendable keys, else 0
   const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
   const uint32_t sLse = sAdd + 128 * 4;        // [384] f32: log-sum-exp of every query of this (b,h)
@@ -137,8 +137,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(s_bar, 1);
     mbar_init(pds_bar, kBwdComputeWarps);
     mbar_init(g_bar, 1);
-    mbar_init(&dq_bar[0], 1);
-    mbar_init(&dq_bar[1], 1);
+    mbar_init(dq_bar, 1);
     fence_barrier_init();
   }
   if (is_control) {
@@ -153,7 +152,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256,
-                 tdK = tmem_base + 320, tdQ = tmem_base + 384;   // tdQ: two 64-column buffers
+                 tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
   const int ntiles = (p.n + kBT - 1) / kBT;
   const int pairs_per_bh = ntiles * ntiles;
@@ -166,104 +165,116 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   if (is_control) {
     // ===================== control warp =====================
     if (lane == 0) {
-      auto decode = [&](int pc, int& bh, int& j, int& i) {
-        const int k = pc / pairs_per_bh, r = pc % pairs_per_bh;
-        bh = blockIdx.x + k * gridDim.x;
-        j = r / ntiles;
-        i = r % ntiles;
+      // Coordinates of a pair are tracked incrementally (no divisions on this single-thread
+      // critical path): `cur` is the pair whose gradient MMAs are issued, `nxt` the one whose
+      // tiles are prefetched / whose S,dP are issued, `kvn` the next key step to prefetch.
+      struct Coord { int bh, j, i; };
+      auto advance = [&](Coord& c) {
+        if (++c.i == ntiles) { c.i = 0; if (++c.j == ntiles) { c.j = 0; c.bh += gridDim.x; } }
       };
-      auto load_kv = [&](int pc) {      // pc = first pair of a key step; kc = running key-step id
-        int bh, j, i;
-        decode(pc, bh, j, i);
-        const int kc = pc / ntiles;
-        const int b = bh / p.H, h = bh % p.H;
+      auto load_kv = [&](const Coord& c, int kc) {
+        const int b = c.bh / p.H, h = c.bh - b * p.H;
         uint8_t* dst = sKV + (kc & 1) * 2 * kBBox;
         mbar_arrive_expect_tx(&kv_bar[kc & 1], 2 * kBBox);
-        tma_load_3d(dst, &tm_qkv, &kv_bar[kc & 1], inner + h * kBDh, j * kBT, b);
-        tma_load_3d(dst + kBBox, &tm_qkv, &kv_bar[kc & 1], 2 * inner + h * kBDh, j * kBT, b);
+        tma_load_3d(dst, &tm_qkv, &kv_bar[kc & 1], inner + h * kBDh, c.j * kBT, b);
+        tma_load_3d(dst + kBBox, &tm_qkv, &kv_bar[kc & 1], 2 * inner + h * kBDh, c.j * kBT, b);
       };
-      auto load_qdo = [&](int pc) {
-        int bh, j, i;
-        decode(pc, bh, j, i);
-        const int b = bh / p.H, h = bh % p.H;
+      auto load_qdo = [&](const Coord& c, int pc) {
+        const int b = c.bh / p.H, h = c.bh - b * p.H;
         uint8_t* dst = sQdO + (pc & 1) * 2 * kBBox;
         mbar_arrive_expect_tx(&qdo_bar[pc & 1], 2 * kBBox);
-        tma_load_3d(dst, &tm_qkv, &qdo_bar[pc & 1], h * kBDh, i * kBT, b);
-        tma_load_3d(dst + kBBox, &tm_do, &qdo_bar[pc & 1], h * kBDh, i * kBT, b);
+        tma_load_3d(dst, &tm_qkv, &qdo_bar[pc & 1], h * kBDh, c.i * kBT, b);
+        tma_load_3d(dst + kBBox, &tm_do, &qdo_bar[pc & 1], h * kBDh, c.i * kBT, b);
       };
-      auto issue_scores = [&](int pc) {  // S and dP of pair pc
-        const int kc = pc / ntiles;
-        const int jj = (pc % pairs_per_bh) / ntiles;
+      const uint32_t sKV_a = smem_u32(sKV), sQdO_a = smem_u32(sQdO);
+      // descriptors whose operand never moves: P^T / dS^T (MN-major A) and dS (K-major A)
+      const uint64_t desc_pT = make_smem_desc(smem_u32(sP), kBBox, 1024);
+      const uint64_t desc_dsT = make_smem_desc(smem_u32(sdS), kBBox, 1024);
+      const uint64_t desc_dsK = make_smem_desc(smem_u32(sdS), 0, 1024);
+      auto issue_scores = [&](const Coord& c, int pc, int kc) {  // S and dP of pair pc
         // only the key columns that exist (rounded to 32) are produced for a partial key tile
-        const int vc = min(kBT, (p.n - jj * kBT + 31) / 32 * 32);
+        const int vc = min(kBT, (p.n - c.j * kBT + 31) / 32 * 32);
         const uint32_t idesc = make_idesc_bf16(kBT, vc, kMajorK, kMajorK);
-        const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
-        const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
+        const uint32_t kv = sKV_a + (kc & 1) * 2 * kBBox;
+        const uint32_t qd_ = sQdO_a + (pc & 1) * 2 * kBBox;
         const uint64_t qd = make_smem_desc(qd_, 0, 1024);
         const uint64_t kd = make_smem_desc(kv, 0, 1024);
         const uint64_t dod = make_smem_desc(qd_ + kBBox, 0, 1024);
         const uint64_t vd = make_smem_desc(kv + kBBox, 0, 1024);
 #pragma unroll
-        for (int k = 0; k < kBDh / 16; ++k)
-          umma_bf16(tS, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc, k > 0);
+        for (int k = 0; k < kBDh / 16; ++k) umma_bf16(tS, qd + 2 * k, kd + 2 * k, idesc, k > 0);
 #pragma unroll
-        for (int k = 0; k < kBDh / 16; ++k)
-          umma_bf16(tdP, desc_advance(dod, k * 32), desc_advance(vd, k * 32), idesc, k > 0);
+        for (int k = 0; k < kBDh / 16; ++k) umma_bf16(tdP, dod + 2 * k, vd + 2 * k, idesc, k > 0);
         umma_commit(s_bar);
       };
 
+      Coord cur{(int)blockIdx.x, 0, 0}, nxt = cur, kvn = cur;
       if (my_pairs > 0) {
-        load_kv(0);
-        load_qdo(0);
+        load_kv(cur, 0);
+        load_qdo(cur, 0);
         mbar_wait(&kv_bar[0], 0);
         mbar_wait(&qdo_bar[0], 0);
         tcgen05_fence_after();
-        issue_scores(0);
+        issue_scores(cur, 0, 0);
+        advance(nxt);
+        kvn.j = 1;
+        if (kvn.j == ntiles) { kvn.j = 0; kvn.bh += gridDim.x; }
       }
+      int kc = 0;                       // running key-step id of `cur`
       for (int pc = 0; pc < my_pairs; ++pc) {
-        const int i = pc % ntiles;
-        const int kc = pc / ntiles;
-        const int j = (pc % pairs_per_bh) / ntiles;
+        const int i = cur.i, j = cur.j;
         const int ksteps_q = min(kBT, (p.n - i * kBT + 15) / 16 * 16) / 16;   // valid query groups
         const int ksteps_k = min(kBT, (p.n - j * kBT + 31) / 32 * 32) / 16;   // valid key groups
         const bool has_next = pc + 1 < my_pairs;
         // all MMAs of pair pc-1 retired: its Q/dO buffer and (if it closed a key step) the
         // K/V buffer of that step may be overwritten
         if (pc >= 1) mbar_wait(g_bar, (pc - 1) & 1);
-        if (i == 0 && (kc + 1) * ntiles < my_pairs) load_kv((kc + 1) * ntiles);  // next key step
-        if (has_next) load_qdo(pc + 1);
+        if (i == 0 && (kc + 1) * ntiles < my_pairs) {   // prefetch K/V of the next key step
+          load_kv(kvn, kc + 1);
+          if (++kvn.j == ntiles) { kvn.j = 0; kvn.bh += gridDim.x; }
+        }
+        if (has_next) load_qdo(nxt, pc + 1);
 
         mbar_wait(pds_bar, pc & 1);   // P, dS of pair pc are in smem; S/dP TMEM consumed
         tcgen05_fence_after();
         {
           constexpr uint32_t idesc_t = make_idesc_bf16(kBT, kBDh, kMajorMN, kMajorMN);
           constexpr uint32_t idesc_q = make_idesc_bf16(kBT, kBDh, kMajorK, kMajorMN);
-          const uint32_t kv = smem_u32(sKV + (kc & 1) * 2 * kBBox);
-          const uint32_t qd_ = smem_u32(sQdO + (pc & 1) * 2 * kBBox);
-          for (int k = 0; k < ksteps_k; ++k) {  // dQ first (contraction over the valid keys): its
-            const uint64_t dsk =                // epilogue then overlaps the dV/dK MMAs below
-                make_smem_desc(smem_u32(sdS) + (k >> 2) * kBBox + (k & 3) * 32, 0, 1024);
-            const uint64_t kb = make_smem_desc(kv + k * 2048, 8192, 1024);
-            umma_bf16(tdQ + (pc & 1) * kBDh, dsk, kb, idesc_q, k > 0 ? 1u : 0u);
+          const uint32_t kv = sKV_a + (kc & 1) * 2 * kBBox;
+          const uint32_t qd_ = sQdO_a + (pc & 1) * 2 * kBBox;
+          const uint64_t desc_kmn = make_smem_desc(kv, 8192, 1024);          // K_j, MN-major B
+          const uint64_t desc_qmn = make_smem_desc(qd_, 8192, 1024);         // Q_i, MN-major B
+          const uint64_t desc_domn = make_smem_desc(qd_ + kBBox, 8192, 1024);  // dO_i, MN-major B
+          // dQ first (contraction over the valid keys): its epilogue overlaps the dV/dK MMAs.
+          // Fully unrolled with compile-time offsets; descriptor address units are 16 bytes.
+#pragma unroll
+          for (int k = 0; k < kBT / 16; ++k) {
+            if (k < ksteps_k)
+              umma_bf16(tdQ, desc_dsK + ((k >> 2) * (kBBox >> 4) + (k & 3) * 2),
+                        desc_kmn + k * 128, idesc_q, k > 0 ? 1u : 0u);
           }
-          umma_commit(&dq_bar[pc & 1]);
-          for (int k = 0; k < ksteps_q; ++k) {  // contraction over the valid queries
-            const uint64_t pT = make_smem_desc(smem_u32(sP) + k * 2048, kBBox, 1024);
-            const uint64_t dsT = make_smem_desc(smem_u32(sdS) + k * 2048, kBBox, 1024);
-            const uint64_t dob = make_smem_desc(qd_ + kBBox + k * 2048, 8192, 1024);
-            const uint64_t qb = make_smem_desc(qd_ + k * 2048, 8192, 1024);
-            umma_bf16(tdV, pT, dob, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tdK, dsT, qb, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(dq_bar);
+#pragma unroll
+          for (int k = 0; k < kBT / 16; ++k) {   // contraction over the valid queries
+            if (k < ksteps_q) {
+              umma_bf16(tdV, desc_pT + k * 128, desc_domn + k * 128, idesc_t,
+                        (i > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tdK, desc_dsT + k * 128, desc_qmn + k * 128, idesc_t,
+                        (i > 0 || k > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(g_bar);
         if (has_next) {               // S/dP of the next pair queue right behind
-          const int nkc = (pc + 1) / ntiles;
-          if ((pc + 1) % ntiles == 0) mbar_wait(&kv_bar[nkc & 1], (nkc >> 1) & 1);
+          const int nkc = (nxt.i == 0) ? kc + 1 : kc;
+          if (nxt.i == 0) mbar_wait(&kv_bar[nkc & 1], (nkc >> 1) & 1);
           mbar_wait(&qdo_bar[(pc + 1) & 1], ((pc + 1) >> 1) & 1);
           tcgen05_fence_after();
-          issue_scores(pc + 1);
+          issue_scores(nxt, pc + 1, nkc);
         }
+        advance(cur);
+        advance(nxt);
+        if (cur.i == 0) ++kc;
       }
       if (my_pairs > 0) mbar_wait(g_bar, (my_pairs - 1) & 1);
     }
@@ -273,57 +284,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    // dQ_i partial of one (key tile, query tile) pair: this thread owns 32 of the 64 columns of
-    // its row; partials of earlier key tiles are re-read from the fp32 workspace first.
-    auto dq_epilogue = [&](int eb, int eh, int ei, int ej, int epc) {
-      const int q_idx = ei * kBT + row;
-      const bool q_ok = q_idx < p.n;
-          const long long tok = (long long)eb * p.n + (q_ok ? q_idx : 0);
-          float* ws = p.dq_ws ? p.dq_ws + tok * inner + eh * kBDh + half * 32 : nullptr;
-          float4 prev[8];
-          if (ej > 0 && q_ok) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) prev[e] = *reinterpret_cast<const float4*>(ws + e * 4);
-          }
-          mbar_wait(&dq_bar[epc & 1], (epc >> 1) & 1);
-          tcgen05_fence_after();
-          {
-            uint32_t v[32];
-            tmem_ld_32x32(tdQ + (epc & 1) * kBDh + lane_off + half * 32, v);
-            tmem_ld_wait();
-            if (q_ok) {
-              float f[32];
-#pragma unroll
-              for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-              if (ej > 0) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  f[e * 4] += prev[e].x; f[e * 4 + 1] += prev[e].y;
-                  f[e * 4 + 2] += prev[e].z; f[e * 4 + 3] += prev[e].w;
-                }
-              }
-              if (ej < ntiles - 1) {
-#pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                  *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-              } else {
-                bf16* dst = p.dqkv + tok * p.ld + eh * kBDh + half * 32;
-#pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                  uint4 o;
-                  o.x = pack_bf16x2(f[e], f[e + 1]);
-                  o.y = pack_bf16x2(f[e + 2], f[e + 3]);
-                  o.z = pack_bf16x2(f[e + 4], f[e + 5]);
-                  o.w = pack_bf16x2(f[e + 6], f[e + 7]);
-                  *reinterpret_cast<uint4*>(dst + e) = o;
-                }
-              }
-            }
-          }
-      tcgen05_fence_before();
-    };
-    bool pend_valid = false;
-    int pend_b = 0, pend_h = 0, pend_i = 0, pend_j = 0, pend_pc = 0;
     int pc = 0;
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
       const int b = bh / p.H, h = bh % p.H;
@@ -406,11 +366,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_bar);
 
-          // The dQ epilogue of the PREVIOUS pair runs here, after this pair's P/dS were handed
-          // to the tensor core: its MMAs (and the fp32 partial it re-reads) have had a whole
-          // compute phase to complete, so nothing on this path waits any more.
-          if (pend_valid) dq_epilogue(pend_b, pend_h, pend_i, pend_j, pend_pc);
-          pend_valid = true; pend_b = b; pend_h = h; pend_i = i; pend_j = j; pend_pc = pc;
+          // dQ_i partial for this key tile: this thread owns 32 of the 64 columns of its row.
+          // The fp32 partial of the previous key tiles is fetched BEFORE waiting for the MMAs.
+          const long long tok = (long long)b * p.n + (q_ok ? q_idx : 0);
+          float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + half * 32 : nullptr;
+          float4 prev[8];
+          if (j > 0 && q_ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) prev[e] = *reinterpret_cast<const float4*>(ws + e * 4);
+          }
+          mbar_wait(dq_bar, pc & 1);
+          tcgen05_fence_after();
+          {
+            uint32_t v[32];
+            tmem_ld_32x32(tdQ + lane_off + half * 32, v);
+            tmem_ld_wait();
+            if (q_ok) {
+              float f[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+              if (j > 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e * 4] += prev[e].x; f[e * 4 + 1] += prev[e].y;
+                  f[e * 4 + 2] += prev[e].z; f[e * 4 + 3] += prev[e].w;
+                }
+              }
+              if (j < ntiles - 1) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                  *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+              } else {
+                bf16* dst = p.dqkv + tok * p.ld + h * kBDh + half * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                  uint4 o;
+                  o.x = pack_bf16x2(f[e], f[e + 1]);
+                  o.y = pack_bf16x2(f[e + 2], f[e + 3]);
+                  o.z = pack_bf16x2(f[e + 4], f[e + 5]);
+                  o.w = pack_bf16x2(f[e + 6], f[e + 7]);
+                  *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+              }
+            }
+          }
           tcgen05_fence_before();
         }  // i
 
@@ -442,7 +441,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }  // j
     }
-    if (pend_valid) dq_epilogue(pend_b, pend_h, pend_i, pend_j, pend_pc);
   }
 
   tcgen05_fence_before();

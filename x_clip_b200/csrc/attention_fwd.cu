@@ -184,15 +184,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
     if (is_control) {
       // ===================== control warp: TMA + MMA issue, software pipelined ============
       if (lane == 0) {
+        // operand descriptors are built once; the loops only add compile-time offsets
+        // (descriptor address units are 16 bytes)
+        const uint64_t desc_q0 = make_smem_desc(smem_u32(sQ), 0, 1024);
+        const uint64_t desc_k = make_smem_desc(smem_u32(sK), 0, 1024);
+        const uint64_t desc_p = make_smem_desc(smem_u32(sP), 0, 1024);
+        const uint64_t desc_v = make_smem_desc(smem_u32(sV), 8192, 1024);
+        const int n_lo = min(256, p.nkp), n_hi = p.nkp - n_lo;      // S column chunks (<= 256 each)
+        const uint32_t idesc_lo = make_idesc_bf16(kTile, n_lo, kMajorK, kMajorK);
+        const uint32_t idesc_hi = make_idesc_bf16(kTile, n_hi > 0 ? n_hi : 16, kMajorK, kMajorK);
         auto issue_s = [&](uint32_t tc) {   // S = Q K^T for the tile with running index tc
-          const uint64_t qd = make_smem_desc(smem_u32(sQ + (tc & 1) * kBoxBytes), 0, 1024);
-          for (int c0 = 0; c0 < p.nkp; c0 += 256) {
-            const int nc = min(256, p.nkp - c0);
-            const uint32_t idesc = make_idesc_bf16(kTile, nc, kMajorK, kMajorK);
-            const uint64_t kd = make_smem_desc(smem_u32(sK) + c0 * 128, 0, 1024);
+          const uint64_t qd = desc_q0 + (tc & 1) * (kBoxBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base, qd + 2 * k, desc_k + 2 * k, idesc_lo, k > 0 ? 1u : 0u);
+          if (n_hi > 0) {
 #pragma unroll
             for (int k = 0; k < kDh / 16; ++k)
-              umma_bf16(tmem_base + c0, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc,
+              umma_bf16(tmem_base + 256, qd + 2 * k, desc_k + (256 * 128 >> 4) + 2 * k, idesc_hi,
                         k > 0 ? 1u : 0u);
           }
           umma_commit(s_bar);
@@ -218,13 +227,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
           // O = P V once the softmax warps have written P (and finished reading S)
           mbar_wait(p_bar, tc & 1);
           tcgen05_fence_after();
-          const uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, kMajorK, kMajorMN);
-          const int ksteps = p.nkp / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t pd =
-                make_smem_desc(smem_u32(sP) + (k >> 2) * kBoxBytes + (k & 3) * 32, 0, 1024);
-            const uint64_t vd = make_smem_desc(smem_u32(sV) + k * 2048, 8192, 1024);
-            umma_bf16(tmem_o, pd, vd, idesc_pv, k > 0 ? 1u : 0u);
+          constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, kMajorK, kMajorMN);
+          const int ksteps = p.nkp / 16;          // <= 20 (n <= 320)
+#pragma unroll
+          for (int k = 0; k < 20; ++k) {
+            if (k < ksteps)
+              umma_bf16(tmem_o, desc_p + ((k >> 2) * (kBoxBytes >> 4) + (k & 3) * 2),
+                        desc_v + k * 128, idesc_pv, k > 0 ? 1u : 0u);
           }
           umma_commit(o_bar);
           if (qt + 1 < num_q_tiles) {   // S(next) queues right behind PV(current)
