@@ -145,8 +145,9 @@ int xclip_nce_bwd(const void* a, const void* b, int R, int C, int D, const float
  *          tokens get col_mul 0 / col_add -FLT_MAX, the reference's masked_fill at :810).
  * reduce : out[a,b] = sum_k weights[a*len+k] * seg_max[(a*len+k), b]  ([samples, nseg] or
  *          transposed) - the masked mean over text tokens (:807) / mean over image tokens (:811).
- * nce_fwd/bwd : row-wise InfoNCE / DCL on a [B,B] fp32 similarity matrix (:821-847);
- *          bwd writes g = *gscale * (softmax_row - identity).
+ * nce_fwd/bwd : row-wise InfoNCE / DCL on an [R,C] fp32 similarity matrix (R local texts, C all
+ *          images, positive of row x at column x + diag_off) (:821-847); bwd writes
+ *          g = *gscale * (softmax_row - [positive]).
  * expand : rows [row0,row0+rows) of the backward operand G[R,C] (bf16): at the argmax column
  *          of each (row, sample) the value *temp_exp * wmat[row/rows_per_sample, sample] *
  *          rowscale[row], zero elsewhere; *dtemp += sum w * seg_max.  d rows = G @ b and
@@ -156,10 +157,10 @@ int xclip_filip_segmax(const void* a, const void* b, int R, int C, int D, const 
                        int* seg_arg, xclip_stream_t stream);
 int xclip_filip_reduce(const float* seg_max, const float* weights, int samples, int len, int nseg,
                        float* out, int transpose_out, xclip_stream_t stream);
-int xclip_filip_nce_fwd(const float* s, int B, int dcl, float* lse, float* loss_accum,
-                        float loss_scale, xclip_stream_t stream);
-int xclip_filip_nce_bwd(const float* s, const float* lse, int B, int dcl, const float* gscale,
-                        float* g, xclip_stream_t stream);
+int xclip_filip_nce_fwd(const float* s, int R, int C, int diag_off, int dcl, float* lse,
+                        float* loss_accum, float loss_scale, xclip_stream_t stream);
+int xclip_filip_nce_bwd(const float* s, const float* lse, int R, int C, int diag_off, int dcl,
+                        const float* gscale, float* g, xclip_stream_t stream);
 int xclip_filip_expand(const int* seg_arg, const float* seg_max, const float* wmat,
                        const float* rowscale, const float* temp_exp, int row0, int rows,
                        int rows_per_sample, int seg_len, int nseg, void* g, int64_t ldg,

@@ -49,5 +49,7 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_oracle():
+    import re
     for f in (ROOT / "x_clip_b200").rglob("*.py"):
-        assert "oracle" not in f.read_text().replace("# oracle", ""), f
+        assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle", f.read_text(), re.M), f
+        assert "oracle" not in f.read_text(), f   # not even mentioned: keeps the boundary obvious

@@ -76,3 +76,29 @@ def test_single_process_is_passthrough():
     a = torch.randn(4, 8)
     assert torch.equal(D.gather_rows([a])[0], a)
     assert D.gather_stats(a) is a
+
+
+def _rs_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from x_clip_b200 import distributed as D
+    t = torch.arange(world * 3 * 4, dtype=torch.float32).view(world * 3, 4) * (rank + 1)
+    out = D.reduce_scatter_rows(t)
+    full = torch.arange(world * 3 * 4, dtype=torch.float32).view(world * 3, 4) * sum(range(1, world + 1))
+    q.put((rank, torch.equal(out, full[rank * 3:(rank + 1) * 3])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reduce_scatter_rows_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rs_worker, args=(r, world, 29735, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(ok for _, ok in res)

@@ -35,39 +35,43 @@ filip_reduce_kernel(const float* __restrict__ m, const float* __restrict__ w, in
   else out[(long long)a * nseg + b] = acc;
 }
 
-// one warp per row of a [B,B] fp32 matrix: lse (optionally without the diagonal), loss partial
+// one warp per row of an [R,C] fp32 matrix (R local texts x C global images; the positive of row
+// x is column x + diag_off): lse (optionally without the positive), loss partial
 __global__ void __launch_bounds__(256)
-filip_nce_fwd_kernel(const float* __restrict__ s, int B, int dcl, float* __restrict__ lse,
-                     float* __restrict__ loss_accum, float scale) {
+filip_nce_fwd_kernel(const float* __restrict__ s, int R, int C, int diag_off, int dcl,
+                     float* __restrict__ lse, float* __restrict__ loss_accum, float scale) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= B) return;
-  const float* r = s + (long long)row * B;
+  if (row >= R) return;
+  const float* r = s + (long long)row * C;
+  const int pos = row + diag_off;
   float mx = -INFINITY;
-  for (int c = lane; c < B; c += 32)
-    if (!(dcl && c == row)) mx = fmaxf(mx, r[c]);
+  for (int c = lane; c < C; c += 32)
+    if (!(dcl && c == pos)) mx = fmaxf(mx, r[c]);
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int c = lane; c < B; c += 32)
-    if (!(dcl && c == row)) sum += __expf(r[c] - mx);
+  for (int c = lane; c < C; c += 32)
+    if (!(dcl && c == pos)) sum += __expf(r[c] - mx);
   sum = warp_sum(sum);
   if (lane == 0) {
     const float l = mx + logf(sum);
     lse[row] = l;
-    if (loss_accum) atomicAdd(loss_accum, (l - r[row]) * scale);
+    if (loss_accum) atomicAdd(loss_accum, (l - r[pos]) * scale);
   }
 }
 
-// g[x,y] = gscale * (exp(s - lse_x) [skipped on the diagonal when dcl] - [x == y])
+// g[x,y] = gscale * (exp(s - lse_x) [skipped on the positive when dcl] - [y == x + diag_off])
 __global__ void __launch_bounds__(256)
-filip_nce_bwd_kernel(const float* __restrict__ s, const float* __restrict__ lse, int B, int dcl,
-                     const float* __restrict__ gscale, float* __restrict__ g) {
+filip_nce_bwd_kernel(const float* __restrict__ s, const float* __restrict__ lse, int R, int C,
+                     int diag_off, int dcl, const float* __restrict__ gscale,
+                     float* __restrict__ g) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * B) return;
-  const int x = (int)(idx / B), y = (int)(idx % B);
+  if (idx >= (long long)R * C) return;
+  const int x = (int)(idx / C), y = (int)(idx % C);
+  const bool is_pos = (y == x + diag_off);
   float v = 0.f;
-  if (!(dcl && x == y)) v = __expf(s[idx] - lse[x]);
-  if (x == y) v -= 1.f;
+  if (!(dcl && is_pos)) v = __expf(s[idx] - lse[x]);
+  if (is_pos) v -= 1.f;
   g[idx] = v * __ldg(gscale);
 }
 
@@ -169,25 +173,26 @@ extern "C" int xclip_filip_reduce(const float* seg_max, const float* weights, in
   return XCLIP_OK;
 }
 
-extern "C" int xclip_filip_nce_fwd(const float* s, int B, int dcl, float* lse, float* loss_accum,
-                                   float loss_scale, xclip_stream_t stream) {
+extern "C" int xclip_filip_nce_fwd(const float* s, int R, int C, int diag_off, int dcl, float* lse,
+                                   float* loss_accum, float loss_scale, xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
-  XCLIP_REQUIRE(s && lse && B > 0, "filip_nce_fwd: bad arguments");
-  filip_nce_fwd_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      s, B, dcl, lse, loss_accum, loss_scale);
+  XCLIP_REQUIRE(s && lse && R > 0 && C > 0 && diag_off >= 0 && diag_off + R <= C,
+                "filip_nce_fwd: bad arguments");
+  filip_nce_fwd_kernel<<<(R + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s, R, C, diag_off, dcl, lse, loss_accum, loss_scale);
   XCLIP_LAUNCH_CHECK("filip_nce_fwd_kernel");
   return XCLIP_OK;
 }
 
-extern "C" int xclip_filip_nce_bwd(const float* s, const float* lse, int B, int dcl,
-                                   const float* gscale, float* g, xclip_stream_t stream) {
+extern "C" int xclip_filip_nce_bwd(const float* s, const float* lse, int R, int C, int diag_off,
+                                   int dcl, const float* gscale, float* g, xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
-  XCLIP_REQUIRE(s && lse && gscale && g && B > 0, "filip_nce_bwd: bad arguments");
-  const long long n = (long long)B * B;
+  XCLIP_REQUIRE(s && lse && gscale && g && R > 0 && C > 0, "filip_nce_bwd: bad arguments");
+  const long long n = (long long)R * C;
   filip_nce_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      s, lse, B, dcl, gscale, g);
+      s, lse, R, C, diag_off, dcl, gscale, g);
   XCLIP_LAUNCH_CHECK("filip_nce_bwd_kernel");
   return XCLIP_OK;
 }

@@ -53,3 +53,19 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if world()[1] > 1:
         dist.all_reduce(t)
     return t
+
+
+def reduce_scatter_rows(t: torch.Tensor) -> torch.Tensor:
+    """t [W*r, D] holds this rank's partial sums for every rank's rows; returns the summed
+    [r, D] block of this rank (FILIP: gradients of the gathered image-token latents)."""
+    rank, w = world()
+    if w == 1:
+        return t
+    rows = t.shape[0] // w
+    t = t.contiguous()
+    if dist.get_backend() == "gloo":          # gloo has no reduce_scatter: all-reduce + slice
+        dist.all_reduce(t)
+        return t[rank * rows:(rank + 1) * rows].clone()
+    out = torch.empty((rows,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+    dist.reduce_scatter_tensor(out, t)
+    return out

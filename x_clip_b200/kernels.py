@@ -286,19 +286,20 @@ def filip_reduce(seg_max, weights, samples, length, nseg, transpose):
     return out
 
 
-def filip_nce_fwd(s, dcl, loss_accum, loss_scale):
-    B = s.shape[0]
-    lse = torch.empty((B,), device=s.device, dtype=F32)
-    _call("filip_small", 0.0, 4.0 * s.numel(), "xclip_filip_nce_fwd", s.data_ptr(), B,
-          1 if dcl else 0, lse.data_ptr(), _ptr(loss_accum), float(loss_scale), _stream())
+def filip_nce_fwd(s, diag_off, dcl, loss_accum, loss_scale):
+    R, C = s.shape
+    lse = torch.empty((R,), device=s.device, dtype=F32)
+    _call("filip_small", 0.0, 4.0 * s.numel(), "xclip_filip_nce_fwd", s.data_ptr(), R, C,
+          int(diag_off), 1 if dcl else 0, lse.data_ptr(), _ptr(loss_accum), float(loss_scale),
+          _stream())
     return lse
 
 
-def filip_nce_bwd(s, lse, dcl, gscale):
-    B = s.shape[0]
+def filip_nce_bwd(s, lse, diag_off, dcl, gscale):
+    R, C = s.shape
     g = torch.empty_like(s)
-    _call("filip_small", 0.0, 8.0 * s.numel(), "xclip_filip_nce_bwd", s.data_ptr(), lse.data_ptr(), B,
-          1 if dcl else 0, gscale.data_ptr(), g.data_ptr(), _stream())
+    _call("filip_small", 0.0, 8.0 * s.numel(), "xclip_filip_nce_bwd", s.data_ptr(), lse.data_ptr(), R,
+          C, int(diag_off), 1 if dcl else 0, gscale.data_ptr(), g.data_ptr(), _stream())
     return g
 
 
