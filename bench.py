@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU")
     ap.add_argument("--patch-dropout", type=float, default=0.5)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--loss", default="nce", choices=["nce", "dcl_extra", "filip"],
+                    help="nce: plain InfoNCE (BASELINE cfg2/3); dcl_extra: decoupled loss + extra latent "
+                         "projections (cfg5); filip: use_all_token_embeds (cfg4)")
     ap.add_argument("--microbatch", type=int, default=0,
                     help="encoder micro-batch (GradCache-style step) - lets --batch 4096 fit one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,7 +213,9 @@ def main():
     B = args.batch
     torch.manual_seed(0)
     model_cfg, workload_txt = WORKLOADS[args.workload]
-    clip = x_clip_b200.CLIP(**model_cfg, visual_patch_dropout=args.patch_dropout,
+    loss_kw = {"nce": {}, "dcl_extra": dict(decoupled_contrastive_learning=True, extra_latent_projection=True),
+               "filip": dict(use_all_token_embeds=True)}[args.loss]
+    clip = x_clip_b200.CLIP(**model_cfg, **loss_kw, visual_patch_dropout=args.patch_dropout,
                             microbatch=args.microbatch or None).to(dev)
     clip.train()
     params = [p for p in clip.parameters()]
@@ -384,7 +389,9 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_txt.format(b=B, pd=args.patch_dropout) + (f", encoder micro-batch {args.microbatch} "
+        "config": {"workload": workload_txt.format(b=B, pd=args.patch_dropout).replace(
+                       "plain InfoNCE", {"nce": "plain InfoNCE", "dcl_extra": "DCL + extra latent projection",
+                                         "filip": "FILIP (use_all_token_embeds)"}[args.loss]) + (f", encoder micro-batch {args.microbatch} "
                    "(two-pass GradCache step: +1 encoder forward)" if args.microbatch else ""),
                    "global_batch": Bg, "parallelism": f"dp{world}",
                    "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed",
