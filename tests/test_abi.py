@@ -32,8 +32,8 @@ def test_version_and_error_string_without_gpu():
     lib = _lib.load()
     assert lib.xclip_abi_version() == 1
     assert isinstance(lib.xclip_last_error(), bytes)
-    assert lib.xclip_nce_num_col_blocks(1024) == 8
-    assert lib.xclip_nce_num_col_blocks(100) == 2
+    assert lib.xclip_nce_num_col_blocks(1024) == 4
+    assert lib.xclip_nce_num_col_blocks(100) == 1
 
 
 def test_no_cpu_fallback():

@@ -11,11 +11,10 @@
 // This one kernel covers the reference's nn.Linear call sites on the hot path
 // (x_clip/x_clip.py:191,195,209,210,358,368,556,570) and their autograd backward.
 //
-// Structure (one CTA per SM, 320 threads):
-//   warps 0-7 : epilogue  (TMEM -> registers -> smem/global; warps w and w+4 share TMEM lanes
-//               32(w%4)..+31 and split the tile's columns in alternating 64-wide groups)
-//   warp  8   : TMA producer (one elected lane)
-//   warp  9   : TMEM allocator + MMA issuer (one lane issues tcgen05.mma / tcgen05.commit)
+// Structure (one CTA per SM, 192 threads):
+//   warps 0-3 : epilogue  (TMEM -> registers -> global; warp w owns TMEM lanes 32w..32w+31)
+//   warp  4   : TMA producer (one elected lane)
+//   warp  5   : TMEM allocator + MMA issuer (one lane issues tcgen05.mma / tcgen05.commit)
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulators double-buffered
 // full/empty (MMA <-> epilogue), static persistent tile scheduler with optional split-K.
 #pragma once
@@ -67,8 +66,7 @@ constexpr int EPI_SEGMAX = 3;   // per row and column segment: max and argmax of
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
-constexpr int kGemmEpiWarps = 8;                       // two warps per TMEM lane quarter
-constexpr int kGemmThreads = (kGemmEpiWarps + 2) * 32;  // + TMA producer warp + MMA issuer warp
+constexpr int kGemmThreads = 192;
 
 template <int BLOCK_N>
 struct GemmSmem {
@@ -123,22 +121,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kGemmEpiWarps);
+      mbar_init(&tmem_empty[i], 4);
     }
     fence_barrier_init();
   }
-  if (warp == kGemmEpiWarps && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.use_tma_store) tma_prefetch_desc(&tmC);
   }
-  if (warp == kGemmEpiWarps + 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kGemmEpiWarps) {
+  if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -175,7 +173,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == kGemmEpiWarps + 1) {
+  } else if (warp == 5) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
     // K-major: SBO = 1024 (8 rows x 128 B), LBO unused.  MN-major: SBO = 1024 between
@@ -220,10 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue (warps 0-3) =====================
     int it = 0;
-    // Two warps share each TMEM lane quarter (warp w and w+4) and split the tile's columns in
-    // 64-wide groups: group 0 (warps 0-3) takes the even 64-column quarters, group 1 the odd ones.
-    const int quarter = warp & 3;
-    const int grp = warp >> 2;
+    uint32_t store_count = 0;   // staging-buffer parity of the TMA-store path
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tmn = t % (num_n * num_m);
       const int n_blk = p.raster_m_fast ? tmn / num_m : tmn % num_n;
@@ -237,9 +232,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
 
-      const int row = m_blk * kGemmBlockM + quarter * 32 + lane;
+      const int row = m_blk * kGemmBlockM + warp * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BLOCK_N;
       const bf16* res_row = nullptr;
       if (p.residual != nullptr && row_ok) {
         const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
@@ -249,14 +244,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.use_tma_store) {
           // bf16 output: 64-column boxes staged in swizzled smem (double buffered), written by
           // cp.async.bulk.tensor stores (full-line writes, no LSU pressure, tails clipped by TMA)
-          // each group owns one 16 KiB staging box and its own bulk-store stream
-          const int row_in_tile = quarter * 32 + lane;
-          const bool issuer = (threadIdx.x == grp * 128);
-          const uint32_t stg = smem_u32(smem_c) + grp * 16384;
+          const int row_in_tile = warp * 32 + lane;
 #pragma unroll 1
-          for (int q = grp; q < BLOCK_N / 64; q += 2) {
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          for (int q = 0; q < BLOCK_N / 64; ++q) {
+            const uint32_t stg = smem_u32(smem_c) + (store_count & 1) * 16384;
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
             for (int c32 = 0; c32 < 2; ++c32) {
               uint32_t v[32];
@@ -299,8 +292,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             fence_proxy_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-            if (issuer) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
               const int c0 = n_blk * BLOCK_N + q * 64;
               if (c0 < p.N) {
                 asm volatile(
@@ -311,11 +304,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            ++store_count;
           }
         } else {
   #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
-          if (((c >> 1) & 1) != grp) continue;
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -389,7 +382,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float rsum = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
-          if (((c >> 1) & 1) != grp) continue;
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -403,16 +395,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (col < p.N && !(p.dcl && is_diag)) rsum += exp2f(acc_v * a2 - a2);
           }
         }
-        if (row_ok) p.nce_part[(long long)(n_blk * 2 + grp) * p.M + row] = rsum;   // 2 partials / block
+        if (row_ok) p.nce_part[(long long)n_blk * p.M + row] = rsum;
       } else if constexpr (EPI == EPI_SEGMAX) {
         const float alpha = __ldg(p.alpha_dev);
         const int col_base = n_blk * n_stride;
         const int valid = min(n_stride, p.N - col_base);        // multiple of seg_len (and of 16)
         float best = -INFINITY;
         int best_i = 0;
-        // segments may span 64-column groups: the running max stays with group 0's warps
 #pragma unroll 1
-        for (int c0 = 0; c0 < (grp == 0 ? valid : 0); c0 += 16) {
+        for (int c0 = 0; c0 < valid; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c0, v);
           tmem_ld_wait();
@@ -442,7 +433,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float tsum = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
-          if (((c >> 1) & 1) != grp) continue;
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -489,13 +479,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (EPI == EPI_STORE && p.use_tma_store && (threadIdx.x & 127) == 0)
+    if (EPI == EPI_STORE && p.use_tma_store && threadIdx.x == 0)
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kGemmEpiWarps + 1) {
+  if (warp == 5) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }

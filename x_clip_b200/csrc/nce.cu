@@ -84,10 +84,7 @@ static int nce_common(const void* a, const void* b, int R, int C, int D, GemmPar
 
 using namespace xclip;
 
-// partial-sum slots per row: two (one per epilogue column group) for every column block
-extern "C" int xclip_nce_num_col_blocks(int C) {
-  return 2 * (C >= 256 ? (C + 255) / 256 : (C + 127) / 128);
-}
+extern "C" int xclip_nce_num_col_blocks(int C) { return C >= 256 ? (C + 255) / 256 : (C + 127) / 128; }
 
 extern "C" int xclip_nce_fwd(const void* a, const void* b, int R, int C, int D,
                              const float* temp_exp,
