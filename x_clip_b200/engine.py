@@ -57,6 +57,40 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# Weight gradients are off the critical path of the backward chain (nothing downstream reads
+# them), so the transformer backward launches them on a side stream: the tensor-bound wgrad GEMM
+# then overlaps with the HBM-bound LayerNorm / GEGLU backward kernels of the main stream (those
+# need < 3 KB of shared memory and co-reside with the persistent GEMM CTAs).
+OVERLAP_WGRAD = True
+_side_streams = {}
+
+
+class _WgradStream:
+    def __init__(self, device: torch.device):
+        self.enabled = OVERLAP_WGRAD
+        self.main = torch.cuda.current_stream(device)
+        if self.enabled:
+            key = (device.index, self.main.cuda_stream)
+            if key not in _side_streams:
+                _side_streams[key] = torch.cuda.Stream(device=device)
+            self.side = _side_streams[key]
+
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        if not self.enabled:
+            return _wgrad(dy, x)
+        out = torch.zeros((dy.shape[1], x.shape[1]), device=dy.device, dtype=F32)
+        self.side.wait_stream(self.main)          # operands (and the zero fill) are ready
+        with torch.cuda.stream(self.side):
+            K.gemm(dy, x, a_major=1, b_major=1, out=out, accumulate=True)
+        for t in (dy, x, out):                    # keep the allocator from recycling them early
+            t.record_stream(self.side)
+        return out
+
+    def join(self) -> None:
+        if self.enabled:
+            self.main.wait_stream(self.side)
+
+
 class LayerWeights:
     """fp32 parameters of one transformer layer, in the order TransformerFn receives them."""
     FIELDS = ("g1", "wqkv", "wo", "go", "g2", "w1", "g4", "w2")
@@ -121,6 +155,7 @@ class TransformerFn(torch.autograd.Function):
         dout = dout.contiguous()
 
         grads: List[Optional[torch.Tensor]] = [None] * len(weights)
+        wg = _WgradStream(dev)
         dg_out = torch.zeros(d, device=dev, dtype=F32)
         dx = K.layernorm_bwd(dout, x_last, st_out, g_out, dg=dg_out)
         grads[1] = dg_out
@@ -131,13 +166,13 @@ class TransformerFn(torch.autograd.Function):
             base = 2 + 8 * L
             # feed-forward: x2 = h @ w2^T + x1
             dh = K.gemm(dx, weight_bf16(w2), b_major=1)
-            grads[base + 7] = _wgrad(dx, h)
+            grads[base + 7] = wg.wgrad(dx, h)
             dg4 = torch.zeros(g4.shape[0], device=dev, dtype=F32)
             du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
             grads[base + 6] = dg4
             del dh
             dxn2 = K.gemm(du, weight_bf16(w1), b_major=1)
-            grads[base + 5] = _wgrad(du, xn2)
+            grads[base + 5] = wg.wgrad(du, xn2)
             del du
             dg2 = torch.zeros(d, device=dev, dtype=F32)
             dx1 = K.layernorm_bwd(dxn2, x1, st_x1, g2, add=dx, dg=dg2)
@@ -147,16 +182,17 @@ class TransformerFn(torch.autograd.Function):
             dy = K.layernorm_bwd(dx1, y, st_y, go, dg=dgo)
             grads[base + 3] = dgo
             d_o = K.gemm(dy, weight_bf16(wo), b_major=1)
-            grads[base + 2] = _wgrad(dy, o)
+            grads[base + 2] = wg.wgrad(dy, o)
             dqkv = K.attn_bwd(qkv, ctx.mask, o, d_o, lse, B, n, heads, scale)
             dxn = K.gemm(dqkv, weight_bf16(wqkv), b_major=1)
-            grads[base + 1] = _wgrad(dqkv, xn)
+            grads[base + 1] = wg.wgrad(dqkv, xn)
             dg1 = torch.zeros(d, device=dev, dtype=F32)
             dx = K.layernorm_bwd(dxn, xcur, st1, g1, add=dx1, dg=dg1)
             grads[base + 0] = dg1
         dg_in = torch.zeros(d, device=dev, dtype=F32)
         dx_in = K.layernorm_bwd(dx, x_in, st_in, g_in, dg=dg_in)
         grads[0] = dg_in
+        wg.join()
         ctx.saved = None
         return (dx_in.view(B, n, d), None, None, None, *grads)
 
