@@ -61,7 +61,7 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 # them), so the transformer backward launches them on a side stream: the tensor-bound wgrad GEMM
 # then overlaps with the HBM-bound LayerNorm / GEGLU backward kernels of the main stream (those
 # need < 3 KB of shared memory and co-reside with the persistent GEMM CTAs).
-OVERLAP_WGRAD = True
+OVERLAP_WGRAD = False   # measured neutral at cfg2 (82.9 vs 82.5 ms): the persistent GEMM leaves no room to co-schedule
 _side_streams = {}
 
 
