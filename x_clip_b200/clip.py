@@ -21,7 +21,6 @@ import torch.distributed as dist
 from torch import nn
 
 from . import engine as E
-from . import kernels as K
 
 BF16 = torch.bfloat16
 

@@ -12,12 +12,11 @@ nn.Linear :358,:368 (LinearFn), :713-724 (ProjectL2NormFn), :759-769 + :797-847
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import weakref
 
 import torch
-import torch.distributed as dist
 
 from . import kernels as K
 from . import distributed as D_
@@ -89,11 +88,6 @@ class _WgradStream:
     def join(self) -> None:
         if self.enabled:
             self.main.wait_stream(self.side)
-
-
-class LayerWeights:
-    """fp32 parameters of one transformer layer, in the order TransformerFn receives them."""
-    FIELDS = ("g1", "wqkv", "wo", "go", "g2", "w1", "g4", "w2")
 
 
 class TransformerFn(torch.autograd.Function):
