@@ -83,14 +83,27 @@ ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int warp_stride = gridDim.x * kRowWarps;
+  constexpr bool kPipelined = NV <= 2;
+  uint4 nx[NV];
+  if (kPipelined && warp_global < rows) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      nx[j] = *reinterpret_cast<const uint4*>(x + warp_global * ldx + (j * 32 + lane) * 8);
+  }
   for (int row = warp_global; row < rows; row += warp_stride) {
     float v[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      load8(x + row * ldx + (j * 32 + lane) * 8, v[j]);
+      if (kPipelined) unpack8(nx[j], v[j]);
+      else load8(x + row * ldx + (j * 32 + lane) * 8, v[j]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += v[j][e];
+    }
+    if (kPipelined && row + warp_stride < rows) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        nx[j] = *reinterpret_cast<const uint4*>(x + (row + warp_stride) * ldx + (j * 32 + lane) * 8);
     }
     const float mean = warp_sum(s) * (1.f / D);
     float q = 0.f;
@@ -328,7 +341,7 @@ geglu_ln_fwd_kernel(const bf16* __restrict__ u, long long ldu, const float* __re
 }
 
 template <int THREADS>  // THREADS = DH / 8
-__global__ void __launch_bounds__(THREADS, (768 / THREADS) > 0 ? (768 / THREADS) : 1)
+__global__ void __launch_bounds__(THREADS, (1024 / THREADS) > 0 ? (1024 / THREADS) : 1)
 geglu_ln_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __restrict__ u,
                     long long ldu, const float* __restrict__ stats, const float* __restrict__ g,
                     bf16* __restrict__ du, long long lddu, float* __restrict__ dg, int rows) {
