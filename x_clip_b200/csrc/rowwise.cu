@@ -341,7 +341,7 @@ geglu_ln_fwd_kernel(const bf16* __restrict__ u, long long ldu, const float* __re
 }
 
 template <int THREADS>  // THREADS = DH / 8
-__global__ void __launch_bounds__(THREADS, (1024 / THREADS) > 0 ? (1024 / THREADS) : 1)
+__global__ void __launch_bounds__(THREADS, (768 / THREADS) > 0 ? (768 / THREADS) : 1)
 geglu_ln_bwd_kernel(const bf16* __restrict__ dh, long long lddh, const bf16* __restrict__ u,
                     long long ldu, const float* __restrict__ stats, const float* __restrict__ g,
                     bf16* __restrict__ du, long long lddu, float* __restrict__ dg, int rows) {
