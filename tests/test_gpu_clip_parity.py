@@ -181,3 +181,69 @@ def test_microbatched_step_equals_single_pass(cuda_device):
         out.append((loss.item(), clip.to_visual_latent.weight.grad.clone()))
     assert out[0][0] == out[1][0] and torch.isfinite(out[0][1]).all()
     assert (out[0][1] - out[1][1]).abs().max().item() <= 1e-3 * out[0][1].abs().max().item()
+
+
+def test_pluggable_encoders_freeze_and_maskless(cuda_device):
+    """Hooks of the reference surface (x_clip.py:482-483, 501-502, 604-605, 659-660): foreign
+    encoders returning [B,n,d] / [B,d], freeze_* flags, text_encode_without_mask."""
+    from oracle import clip_oracle as O
+    import x_clip_b200
+    dev = cuda_device
+    gold = json.loads((GOLD / "tiny_plain.json").read_text())
+    cfg = O.ClipConfig(**gold["cfg"])
+    text, image = O.protocol_inputs(cfg, 4, 4321, 0.2)
+    text, image = text.to(dev), image.to(dev)
+
+    class TextEnc(torch.nn.Module):                 # returns [B, 1+n, d], CLS at index 0
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(128, 256)
+        def forward(self, ids, mask=None):
+            h = self.emb(ids)
+            return torch.cat((h.mean(1, keepdim=True), h), dim=1)
+
+    class ImageEnc(torch.nn.Module):                # returns [B, d]
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(3 * 64 * 64, 256)
+        def forward(self, img):
+            return self.lin(img.flatten(1))
+
+    torch.manual_seed(0)
+    clip = x_clip_b200.CLIP(**gold["cfg"], text_encoder=TextEnc(), image_encoder=ImageEnc()).to(dev)
+    clip.train()
+    loss = clip(text, image, return_loss=True)
+    loss.backward()
+    assert torch.isfinite(loss) and clip.text_transformer.emb.weight.grad.abs().sum() > 0
+    assert clip.visual_transformer.lin.weight.grad.abs().sum() > 0
+    # reference semantics of the same head on the same encodings (fp32 torch)
+    with torch.no_grad():
+        et, ei = clip(text, image, return_encodings=True)
+        zt = torch.nn.functional.normalize(et[:, 0] @ clip.to_text_latent.weight.t(), dim=-1)
+        zi = torch.nn.functional.normalize(ei @ clip.to_visual_latent.weight.t(), dim=-1)
+        ref = O.contrastive_loss(zt.cpu(), zi.cpu(), zt.cpu(), zi.cpu(), clip.temperature.detach().cpu(), cfg)
+    assert abs(loss.item() - ref.item()) <= 2e-3 * abs(ref.item())
+
+    # freeze flags: no gradient reaches the frozen tower
+    clip2 = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0.).to(dev)
+    clip2.load_state_dict(O.protocol_state_dict(cfg, 1234))
+    clip2.train()
+    l2 = clip2(text, image, return_loss=True, freeze_image_encoder=True)
+    l2.backward()
+    assert all(p.grad is None for p in clip2.visual_transformer.parameters())
+    assert clip2.text_transformer.token_emb.weight.grad is not None
+    assert clip2.to_visual_latent.weight.grad is not None
+
+    # text_encode_without_mask: pads are attended like any token -> equals an all-True mask
+    clip3 = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0., text_encode_without_mask=True).to(dev)
+    clip3.load_state_dict(O.protocol_state_dict(cfg, 1234))
+    clip3.train()
+    l3 = clip3(text, image, return_loss=True)
+    p = {k: v.clone() for k, v in O.protocol_state_dict(cfg, 1234).items()}
+    with torch.no_grad():
+        tcpu, icpu = text.cpu(), image.cpu()
+        enc_t = O.encode_text(tcpu, torch.ones_like(tcpu, dtype=torch.bool), p, cfg)
+        enc_i = O.encode_image(icpu, p, cfg)
+        z = O.project_latents(enc_t, enc_i, p, cfg)
+        ref3 = O.contrastive_loss(*z, p["temperature"], cfg)
+    assert abs(l3.item() - ref3.item()) <= 1e-3 * abs(ref3.item())
