@@ -21,6 +21,8 @@
 //
 // Masking follows the reference exactly: a masked key's score is replaced by -FLT_MAX AFTER
 // scaling (so a fully masked row would give uniform attention); keys beyond n do not exist.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -374,6 +376,326 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Ping-pong variant for 128 < n <= 320 (default; XCLIP_ATTN_PP=0 selects the single-buffer kernel).
+//
+// The keys of a query tile are split in two blocks (w0 + w1 columns).  Two S buffers in TMEM
+// alternate between consecutive blocks (also across tiles and (batch, head) items), so the issue
+// thread always has the NEXT block's S = Q K_blk^T in flight while the softmax warps work on the
+// current one.  Every block keeps its own max / sum and accumulates P_blk V_blk into its own
+// 64-column O buffer taken from a ring of three; nothing is rescaled in TMEM - the epilogue
+// combines the two partial outputs:  O = (2^(m0-m) O0 + 2^(m1-m) O1) / (2^(m0-m) l0 + 2^(m1-m) l1).
+// TMEM: S 2 x 160 + O 3 x 64 = 512 columns.  smem: Q 16 + K 48 + V 48 + 2 P buffers x 48 KiB.
+struct AttnPPParams {
+  int B, H, n, nkp, w0, w1;
+  float scale_log2;
+  const uint8_t* mask;
+  bf16* o;
+  long long ldo;
+  float* lse;
+};
+
+constexpr int kPPSub = 3;                       // 64-key sub-blocks per P buffer (block <= 160 keys)
+constexpr int kPPBuf = kPPSub * kBoxBytes;      // 48 KiB
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nkb = (p.n + kTile - 1) / kTile;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kBoxBytes;
+  uint8_t* sV = sK + nkb * kBoxBytes;
+  uint8_t* sP = sV + nkb * kBoxBytes;           // 2 buffers
+  uint8_t* tail = sP + 2 * kPPBuf;
+  uint64_t* k_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* q_bar = k_bar + 1;
+  uint64_t* s_bar = k_bar + 2;     // [2]
+  uint64_t* p_bar = k_bar + 4;     // [2]
+  uint64_t* o_bar = k_bar + 6;     // [3]
+  uint64_t* v_bar = k_bar + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_bar + 10);
+  const uint32_t sMul = smem_u32(tail + 128);           // [384] f32
+  const uint32_t sAdd = sMul + 384 * 4;                 // [384] f32
+  const uint32_t sMax = sAdd + 384 * 4;                 // [2 block parities][2 halves][128] f32
+  const uint32_t sSum = sMax + 2 * 2 * 128 * 4;         // [4 block slots][2 halves][128] f32
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool is_control = warp == kAttnComputeWarps;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    mbar_init(k_bar, 1);
+    mbar_init(v_bar, 1);
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_bar[i], 1); mbar_init(&p_bar[i], kAttnComputeWarps); }
+    for (int i = 0; i < 3; ++i) mbar_init(&o_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (is_control) {
+    if (lane == 0) tma_prefetch_desc(&tm_qkv);
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // S buffers at columns 0 and 160, O ring at 320 / 384 / 448
+
+  const int T = (p.n + kTile - 1) / kTile;      // query tiles per (b,h); 2 blocks per tile
+  const int inner = p.H * kDh;
+
+  if (is_control) {
+    if (lane == 0) {
+      const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 0, 1024);
+      const uint64_t desc_k = make_smem_desc(smem_u32(sK), 0, 1024);
+      const uint64_t desc_v = make_smem_desc(smem_u32(sV), 8192, 1024);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, kMajorK, kMajorMN);
+      const uint32_t idesc_s0 = make_idesc_bf16(kTile, p.w0, kMajorK, kMajorK);
+      const uint32_t idesc_s1 = make_idesc_bf16(kTile, p.w1, kMajorK, kMajorK);
+      auto issue_pv = [&](uint32_t gb) {        // O[gb % 3] = P(gb) V_blk(gb)
+        const int kb = gb & 1;
+        const int k0 = kb ? p.w0 : 0, W = kb ? p.w1 : p.w0;
+        mbar_wait(&p_bar[gb & 1], (gb >> 1) & 1);
+        tcgen05_fence_after();
+        const uint64_t pd = make_smem_desc(smem_u32(sP) + (gb & 1) * kPPBuf, 0, 1024);
+        const uint64_t vd = desc_v + ((k0 * 128) >> 4);
+        const uint32_t td = tmem_base + 320 + (gb % 3) * kDh;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (k < W / 16)
+            umma_bf16(td, pd + ((k >> 2) * (kBoxBytes >> 4) + (k & 3) * 2), vd + k * 128, idesc_pv,
+                      k > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_bar[gb % 3]);
+      };
+      // K + Q(tile 0) and V of the NEXT (b,h) are fetched as soon as their smem is dead: K/Q after
+      // the last S of this item retired, V after its last PV.
+      auto load_kq = [&](int bh2) {
+        const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+        mbar_arrive_expect_tx(k_bar, nkb * kBoxBytes);
+        for (int i = 0; i < nkb; ++i)
+          tma_load_3d(sK + i * kBoxBytes, &tm_qkv, k_bar, inner + h2 * kDh, i * kTile, b2);
+        mbar_arrive_expect_tx(q_bar, kBoxBytes);
+        tma_load_3d(sQ, &tm_qkv, q_bar, h2 * kDh, 0, b2);
+      };
+      auto load_v = [&](int bh2) {
+        const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+        mbar_arrive_expect_tx(v_bar, nkb * kBoxBytes);
+        for (int i = 0; i < nkb; ++i)
+          tma_load_3d(sV + i * kBoxBytes, &tm_qkv, v_bar, 2 * inner + h2 * kDh, i * kTile, b2);
+      };
+      uint32_t g = 0, tt = 0, kvc = 0;          // global block / tile / (b,h) counters of this CTA
+      const int total = p.B * p.H;
+      if ((int)blockIdx.x < total) { load_kq(blockIdx.x); load_v(blockIdx.x); }
+      for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++kvc) {
+        const int b = bh / p.H, h = bh - b * p.H;
+        const int bh_next = bh + gridDim.x;
+        mbar_wait(k_bar, kvc & 1);
+        for (int t = 0; t < T; ++t) {
+          for (int kb = 0; kb < 2; ++kb, ++g) {
+            const int k0 = kb ? p.w0 : 0;
+            if (kb == 0) { mbar_wait(q_bar, tt & 1); ++tt; }
+            if (g >= 2) mbar_wait(&p_bar[g & 1], ((g - 2) >> 1) & 1);   // S[g&1] consumed
+            tcgen05_fence_after();
+            {
+              const uint64_t kd = desc_k + ((k0 * 128) >> 4);
+              const uint32_t ts = tmem_base + (g & 1) * 160;
+              const uint32_t idesc = kb ? idesc_s1 : idesc_s0;
+#pragma unroll
+              for (int k = 0; k < kDh / 16; ++k)
+                umma_bf16(ts, desc_q + 2 * k, kd + 2 * k, idesc, k > 0 ? 1u : 0u);
+              umma_commit(&s_bar[g & 1]);
+            }
+            if (kb == 1) {
+              if (t + 1 < T) {                  // Q(t) is dead once S(g) retired: fetch Q(t+1)
+                mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+                mbar_arrive_expect_tx(q_bar, kBoxBytes);
+                tma_load_3d(sQ, &tm_qkv, q_bar, h * kDh, (t + 1) * kTile, b);
+              } else if (bh_next < total) {     // K and Q of this item are dead
+                mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+                load_kq(bh_next);
+              }
+            }
+            if (t == 0 && kb == 1) mbar_wait(v_bar, kvc & 1);
+            if (!(t == 0 && kb == 0)) issue_pv(g - 1);   // PV lags S by one block
+          }
+        }
+        issue_pv(g - 1);
+        // V / P smem are reused by the next (b,h): wait until the last PV retired
+        mbar_wait(&o_bar[(g - 1) % 3], ((g - 1) / 3) & 1);
+        if (bh_next < total) load_v(bh_next);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue warps =====================
+    const int half = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t g = 0;
+    for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
+      const int b = bh / p.H, h = bh - b * p.H;
+      for (int j = threadIdx.x; j < 384; j += kAttnComputeWarps * 32) {
+        float mul = 0.f, add = -INFINITY;
+        if (j < p.n) {
+          const bool keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
+          mul = keep ? p.scale_log2 : 0.f;
+          add = keep ? 0.f : -FLT_MAX;
+        }
+        sts_f(sMul + j * 4, mul);
+        sts_f(sAdd + j * 4, add);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+
+      float m_blk[2] = {0.f, 0.f}, l_own[2] = {0.f, 0.f};
+      float pm0 = 0.f, pm1 = 0.f, pl0 = 0.f, pl1 = 0.f;   // previous tile's block statistics
+
+      auto epilogue = [&](int t, uint32_t g0, float m0, float m1, float l0o, float l1o) {
+        const uint32_t g1 = g0 + 1;
+        mbar_wait(&o_bar[g0 % 3], (g0 / 3) & 1);
+        mbar_wait(&o_bar[g1 % 3], (g1 / 3) & 1);
+        tcgen05_fence_after();
+        const int q_idx = t * kTile + row;
+        const float l0 = l0o + lds_f(sSum + (((g0 & 3) * 2 + (half ^ 1)) * 128 + row) * 4);
+        const float l1 = l1o + lds_f(sSum + (((g1 & 3) * 2 + (half ^ 1)) * 128 + row) * 4);
+        const float m = fmaxf(m0, m1);
+        const float a0 = ex2_approx(m0 - m), a1 = ex2_approx(m1 - m);
+        const float L = a0 * l0 + a1 * l1;
+        const float inv = 1.f / L;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(tmem_base + 320 + (g0 % 3) * kDh + lane_off + half * 32, v0);
+        tmem_ld_32x32(tmem_base + 320 + (g1 % 3) * kDh + lane_off + half * 32, v1);
+        tmem_ld_wait();
+        if (q_idx < p.n) {
+          if (half == 0) p.lse[((long long)b * p.H + h) * p.n + q_idx] = m + log2f(L);
+          bf16* dst = p.o + ((long long)b * p.n + q_idx) * p.ldo + h * kDh + half * 32;
+          const float c0 = a0 * inv, c1 = a1 * inv;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              f[e] = __uint_as_float(v0[i + e]) * c0 + __uint_as_float(v1[i + e]) * c1;
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(dst + i) = o;
+          }
+        }
+        tcgen05_fence_before();
+      };
+
+      for (int t = 0; t < T; ++t) {
+        const bool warp_alive = t * kTile + quarter * 32 < p.n;
+        for (int kb = 0; kb < 2; ++kb, ++g) {
+          const int k0 = kb ? p.w0 : 0, W = kb ? p.w1 : p.w0;
+          const int nch = W / 16;
+          const int cb = warp_alive ? (half == 0 ? 0 : (nch + 1) / 2) : 0;
+          const int ce = warp_alive ? (half == 0 ? (nch + 1) / 2 : nch) : 0;
+          const uint32_t ts = tmem_base + (g & 1) * 160 + lane_off;
+          mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+          tcgen05_fence_after();
+          // The thread's share of the block (<= 5 chunks of 16 keys) stays in registers between
+          // the max pass and the exp pass: one TMEM read + one wait per block.
+          const int nc = ce - cb;
+          uint32_t w[5][16];
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            if (q < nc) tmem_ld_32x16(ts + (cb + q) * 16, w[q]);
+          tmem_ld_wait();
+          float m2 = -INFINITY;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            if (q < nc) {
+              const uint32_t ma = sMul + (k0 + (cb + q) * 16) * 4, aa = sAdd + (k0 + (cb + q) * 16) * 4;
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
+                const float t0 = fmaf(__uint_as_float(w[q][i]), mm.x, ad.x);
+                const float t1 = fmaf(__uint_as_float(w[q][i + 1]), mm.y, ad.y);
+                const float t2 = fmaf(__uint_as_float(w[q][i + 2]), mm.z, ad.z);
+                const float t3 = fmaf(__uint_as_float(w[q][i + 3]), mm.w, ad.w);
+                m2 = fmaxf(fmaxf(m2, fmaxf(t0, t1)), fmaxf(t2, t3));
+                w[q][i] = __float_as_uint(t0); w[q][i + 1] = __float_as_uint(t1);
+                w[q][i + 2] = __float_as_uint(t2); w[q][i + 3] = __float_as_uint(t3);
+              }
+            }
+          }
+          sts_f(sMax + (((g & 1) * 2 + half) * 128 + row) * 4, m2);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          m2 = fmaxf(m2, lds_f(sMax + (((g & 1) * 2 + (half ^ 1)) * 128 + row) * 4));
+
+          // P buffer (g&1) was last read by PV(g-2)
+          if (g >= 2) mbar_wait(&o_bar[(g - 2) % 3], ((g - 2) / 3) & 1);
+          float sum = 0.f;
+          const uint32_t pbuf = smem_u32(sP) + (g & 1) * kPPBuf;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            if (q < nc) {
+              const int col = (cb + q) * 16;                // column inside the block
+              const uint32_t blk = pbuf + (col >> 6) * kBoxBytes;
+              const int chunk0 = (col & 63) >> 3;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(__uint_as_float(w[q][hh * 8 + i]) - m2);
+                sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                sts_v4(blk + swz128(row, chunk0 + hh), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                       pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+              }
+            }
+          }
+          sts_f(sSum + (((g & 3) * 2 + half) * 128 + row) * 4, sum);
+          fence_proxy_async_smem();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_bar[g & 1]);
+          m_blk[kb] = m2;
+          l_own[kb] = sum;
+
+          // the previous tile's epilogue runs after this tile's first block was handed over
+          if (kb == 0 && t > 0) epilogue(t - 1, g - 2, pm0, pm1, pl0, pl1);
+        }
+        pm0 = m_blk[0]; pm1 = m_blk[1]; pl0 = l_own[0]; pl1 = l_own[1];
+      }
+      epilogue(T - 1, g - 2, pm0, pm1, pl0, pl1);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (is_control) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, cudaStream_t stream) {
+  AttnPPParams p;
+  p.B = q.B; p.H = q.H; p.n = q.n; p.nkp = q.nkp;
+  p.w0 = ((q.nkp / 2) + 15) / 16 * 16;
+  p.w1 = q.nkp - p.w0;
+  p.scale_log2 = q.scale_log2; p.mask = q.mask; p.o = q.o; p.ldo = q.ldo; p.lse = q.lse;
+  const int nkb = (q.n + kTile - 1) / kTile;
+  const int smem = (1 + 2 * nkb) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 4 * 128 * 4 +
+                   8 * 128 * 4;
+  static bool configured = false;
+  if (!configured) {
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (1 + 6) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 +
+                                        4 * 128 * 4 + 8 * 128 * 4));
+    configured = true;
+  }
+  long long grid = num_sms();
+  if (grid > (long long)q.B * q.H) grid = (long long)q.B * q.H;
+  attn_fwd_pp_kernel<<<(int)grid, kAttnThreads, smem, stream>>>(tm, p);
+  XCLIP_LAUNCH_CHECK("attn_fwd_pp_kernel");
+  return XCLIP_OK;
+}
+
 }  // namespace xclip
 
 using namespace xclip;
@@ -406,6 +728,10 @@ extern "C" int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
   rc = encode_3d_bf16(&tm, qkv, (uint64_t)(3 * heads * kDh), (uint64_t)n, (uint64_t)B,
                       (uint64_t)ld_qkv, (uint64_t)n * ld_qkv, kDh, kTile);
   if (rc) return rc;
+
+  static const bool use_pp = [] { const char* e = getenv("XCLIP_ATTN_PP"); return !(e && e[0] == '0'); }();
+  if (use_pp && n > kTile && p.nkp - ((p.nkp / 2) + 15) / 16 * 16 >= 16)
+    return launch_attn_fwd_pp(tm, p, reinterpret_cast<cudaStream_t>(stream));
 
   const int nkb = (n + kTile - 1) / kTile;
   const int npb = (p.nkp + 63) / 64;
