@@ -16,7 +16,9 @@ def _ref_attention(qkv, mask, B, n, H, scale):
 
 
 CASES = [(2, 33, 4, False), (3, 65, 8, False), (2, 128, 2, True), (2, 17, 4, True),
-         (2, 197, 12, False), (2, 257, 8, True), (1, 320, 2, True), (5, 78, 8, True)]
+         (2, 197, 12, False), (2, 257, 8, True), (1, 320, 2, True), (5, 78, 8, True),
+         # n = 128k+1 takes the tail-token path; 24*8 (b,h) items > 148 CTAs: several items per CTA
+         (2, 129, 4, True), (3, 129, 2, False), (24, 257, 8, True), (20, 257, 8, False)]
 
 
 def _mk(B, n, H, masked, dev, seed=0):

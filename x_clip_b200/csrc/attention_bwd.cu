@@ -41,6 +41,13 @@ struct AttnBwdParams {
   bf16* dqkv;            // [B*n, ld] q | k | v gradients
   long long ld;
   float* dq_ws;          // fp32 [B*n, H*64] or null when n <= 128
+  // Tail mode (n = 128k+1, see attention_tail.cu): tiles cover the tokens [0, nt) with nt = n-1;
+  // token z = n-1 was handled by attn_bwd_tail_kernel, which left (ds^c_t, ds^r_t, p^r_t) in the
+  // first three floats of token t's dq_ws slot.  The epilogues add the rank-1 terms
+  // dQ_t += ds^c_t k_z, dK_t += ds^r_t q_z, dV_t += p^r_t dO_z.
+  int nt, tail;
+  const bf16* qkv; long long ld_qkv;
+  const bf16* d_o; long long lddo;
 };
 
 __device__ __forceinline__ float bwd_ex2(float x) {
@@ -120,6 +127,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
   const uint32_t sLse = sAdd + 128 * 4;        // [384] f32: log-sum-exp of every query of this (b,h)
   const uint32_t sDelta = sLse + 384 * 4;      // [384] f32
+  const uint32_t sTail = sDelta + 384 * 4;     // [3][384] f32: ds^c, ds^r, p^r of every token (tail mode)
+  const uint32_t sVec = sTail + 3 * 384 * 4;   // [3][64] f32: k_z, q_z, dO_z (tail mode)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,7 +163,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256,
                  tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
-  const int ntiles = (p.n + kBT - 1) / kBT;
+  const int ntiles = (p.nt + kBT - 1) / kBT;
   const int pairs_per_bh = ntiles * ntiles;
   const int inner = p.H * kBDh;
   const int num_bh = p.B * p.H;
@@ -193,7 +202,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint64_t desc_dsK = make_smem_desc(smem_u32(sdS), 0, 1024);
       auto issue_scores = [&](const Coord& c, int pc, int kc) {  // S and dP of pair pc
         // only the key columns that exist (rounded to 32) are produced for a partial key tile
-        const int vc = min(kBT, (p.n - c.j * kBT + 31) / 32 * 32);
+        const int vc = min(kBT, (p.nt - c.j * kBT + 31) / 32 * 32);
         const uint32_t idesc = make_idesc_bf16(kBT, vc, kMajorK, kMajorK);
         const uint32_t kv = sKV_a + (kc & 1) * 2 * kBBox;
         const uint32_t qd_ = sQdO_a + (pc & 1) * 2 * kBBox;
@@ -223,8 +232,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       int kc = 0;                       // running key-step id of `cur`
       for (int pc = 0; pc < my_pairs; ++pc) {
         const int i = cur.i, j = cur.j;
-        const int ksteps_q = min(kBT, (p.n - i * kBT + 15) / 16 * 16) / 16;   // valid query groups
-        const int ksteps_k = min(kBT, (p.n - j * kBT + 31) / 32 * 32) / 16;   // valid key groups
+        const int ksteps_q = min(kBT, (p.nt - i * kBT + 15) / 16 * 16) / 16;   // valid query groups
+        const int ksteps_k = min(kBT, (p.nt - j * kBT + 31) / 32 * 32) / 16;   // valid key groups
         const bool has_next = pc + 1 < my_pairs;
         // all MMAs of pair pc-1 retired: its Q/dO buffer and (if it closed a key step) the
         // K/V buffer of that step may be overwritten
@@ -288,27 +297,49 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
       const int b = bh / p.H, h = bh % p.H;
       for (int j = 0; j < ntiles; ++j) {
+        // tail mode: the previous item's last dK/dV epilogue reads sTail / sVec
+        if (p.tail && j == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
         // key-tile tables (all compute threads are past every read of the previous tables:
         // the last read precedes their pds arrive of the previous pair, and bar.sync orders)
         if (threadIdx.x < kBT) {
           const int key = j * kBT + threadIdx.x;
           const bool keep =
-              key < p.n && (p.mask ? (p.mask[(long long)b * p.n + key] != 0) : true);
+              key < p.nt && (p.mask ? (p.mask[(long long)b * p.n + key] != 0) : true);
           bwd_sts_f(sMul + threadIdx.x * 4, keep ? p.scale_log2 : 0.f);
           bwd_sts_f(sAdd + threadIdx.x * 4, keep ? 0.f : -INFINITY);
         }
         if (j == 0) {   // per-(b,h) row statistics: +inf lse -> p = 0 for rows beyond n
           for (int q = threadIdx.x; q < 384; q += kBwdComputeWarps * 32) {
             const long long s_idx = ((long long)b * p.H + h) * p.n + q;
-            bwd_sts_f(sLse + q * 4, q < p.n ? p.lse[s_idx] : INFINITY);
-            bwd_sts_f(sDelta + q * 4, q < p.n ? p.delta[s_idx] : 0.f);
+            bwd_sts_f(sLse + q * 4, q < p.nt ? p.lse[s_idx] : INFINITY);
+            bwd_sts_f(sDelta + q * 4, q < p.nt ? p.delta[s_idx] : 0.f);
+          }
+          if (p.tail) {
+            for (int q = threadIdx.x; q < 384; q += kBwdComputeWarps * 32) {
+              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+              if (q < p.nt) {
+                const float* w = p.dq_ws + ((long long)b * p.n + q) * inner + h * kBDh;
+                c0 = w[0]; c1 = w[1]; c2 = w[2];
+              }
+              bwd_sts_f(sTail + q * 4, c0);
+              bwd_sts_f(sTail + (384 + q) * 4, c1);
+              bwd_sts_f(sTail + (768 + q) * 4, c2);
+            }
+            if (threadIdx.x < 192) {
+              const int which = threadIdx.x >> 6, d = threadIdx.x & 63;
+              const long long z = (long long)b * p.n + (p.n - 1);
+              const bf16 x = which == 0   ? p.qkv[z * p.ld_qkv + inner + h * kBDh + d]     // k_z
+                             : which == 1 ? p.qkv[z * p.ld_qkv + h * kBDh + d]             // q_z
+                                          : p.d_o[z * p.lddo + h * kBDh + d];              // dO_z
+              bwd_sts_f(sVec + threadIdx.x * 4, __bfloat162float(x));
+            }
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
         for (int i = 0; i < ntiles; ++i, ++pc) {
           const int q_idx = i * kBT + row;
-          const bool q_ok = q_idx < p.n;
+          const bool q_ok = q_idx < p.nt;
           float lse_i, delta_i;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lse_i) : "r"(sLse + q_idx * 4));
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(delta_i) : "r"(sDelta + q_idx * 4));
@@ -319,8 +350,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           // Partial tiles: the MMAs only touch query groups < vr16 and key columns < vc32 (see the
           // control warp), and every output row depends on its own operand row only, so warps /
           // chunks that are pure padding skip their math and leave their smem slots untouched.
-          const int vr16 = min(kBT, (p.n - i * kBT + 15) / 16 * 16);
-          const int vc32 = min(kBT, (p.n - j * kBT + 31) / 32 * 32);
+          const int vr16 = min(kBT, (p.nt - i * kBT + 15) / 16 * 16);
+          const int vc32 = min(kBT, (p.nt - j * kBT + 31) / 32 * 32);
           const bool warp_alive = quarter * 32 < vr16;
 #pragma unroll
           for (int cc0 = 0; cc0 < 2; ++cc0) {
@@ -397,6 +428,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 for (int e = 0; e < 32; e += 4)
                   *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
               } else {
+                if (p.tail) {   // + ds^c_i k_z
+                  float cds;
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cds) : "r"(sTail + q_idx * 4));
+#pragma unroll
+                  for (int e = 0; e < 32; e += 4) {
+                    const float4 kz = bwd_lds_f4(sVec + (half * 32 + e) * 4);
+                    f[e] = fmaf(cds, kz.x, f[e]); f[e + 1] = fmaf(cds, kz.y, f[e + 1]);
+                    f[e + 2] = fmaf(cds, kz.z, f[e + 2]); f[e + 3] = fmaf(cds, kz.w, f[e + 3]);
+                  }
+                }
                 bf16* dst = p.dqkv + tok * p.ld + h * kBDh + half * 32;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8) {
@@ -423,7 +464,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             uint32_t v[32];
             tmem_ld_32x32((half == 0 ? tdK : tdV) + lane_off + c * 32, v);
             tmem_ld_wait();
-            if (key < p.n) {
+            if (p.tail && key < p.nt) {   // dK: + ds^r_key q_z   dV: + p^r_key dO_z
+              float coef;
+              asm volatile("ld.shared.f32 %0, [%1];"
+                           : "=f"(coef)
+                           : "r"(sTail + ((half == 0 ? 384 : 768) + key) * 4));
+              const uint32_t vec = sVec + ((half == 0 ? 64 : 128) + c * 32) * 4;
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 x = bwd_lds_f4(vec + e * 4);
+                v[e] = __float_as_uint(fmaf(coef, x.x, __uint_as_float(v[e])));
+                v[e + 1] = __float_as_uint(fmaf(coef, x.y, __uint_as_float(v[e + 1])));
+                v[e + 2] = __float_as_uint(fmaf(coef, x.z, __uint_as_float(v[e + 2])));
+                v[e + 3] = __float_as_uint(fmaf(coef, x.w, __uint_as_float(v[e + 3])));
+              }
+            }
+            if (key < p.nt) {
               bf16* dst = p.dqkv + ((long long)b * p.n + key) * p.ld + (half + 1) * inner +
                           h * kBDh + c * 32;
 #pragma unroll
@@ -450,6 +506,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+int launch_attn_bwd_tail(const void* qkv, long long ld, const uint8_t* mask, const void* d_o,
+                         long long lddo, const float* lse, const float* delta, void* dqkv,
+                         long long ldg, float* ws, int B, int H, int n, float scale,
+                         cudaStream_t stream);
 
 }  // namespace xclip
 
@@ -492,6 +553,15 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
   p.scale_log2 = scale * 1.4426950408889634f;
   p.mask = key_mask; p.lse = lse; p.delta = delta;
   p.dqkv = reinterpret_cast<bf16*>(dqkv); p.ld = ld_dqkv; p.dq_ws = dq_workspace;
+  p.tail = (attn_tail_enabled() && n > kBT && n % kBT == 1) ? 1 : 0;
+  p.nt = p.tail ? n - 1 : n;
+  p.qkv = reinterpret_cast<const bf16*>(qkv); p.ld_qkv = ld_qkv;
+  p.d_o = reinterpret_cast<const bf16*>(d_o); p.lddo = lddo;
+  if (p.tail) {
+    rc = launch_attn_bwd_tail(qkv, ld_qkv, key_mask, d_o, lddo, lse, delta, dqkv, ld_dqkv,
+                              dq_workspace, B, n, heads, scale, s);
+    if (rc) return rc;
+  }
 
   CUtensorMap tq, tdo;
   rc = encode_3d_bf16(&tq, qkv, (uint64_t)(3 * heads * kBDh), (uint64_t)n, (uint64_t)B,
@@ -501,7 +571,7 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
                       (uint64_t)lddo, (uint64_t)n * lddo, kBDh, kBT);
   if (rc) return rc;
 
-  const int smem = 12 * kBBox + 128 + 2 * 128 * 4 + 2 * 384 * 4;
+  const int smem = 12 * kBBox + 128 + 2 * 128 * 4 + 2 * 384 * 4 + 3 * 384 * 4 + 3 * 64 * 4;
   static bool configured = false;
   if (!configured) {
     XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -389,6 +389,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
 // TMEM: S 2 x 160 + O 3 x 64 = 512 columns.  smem: Q 16 + K 48 + V 48 + 2 P buffers x 48 KiB.
 struct AttnPPParams {
   int B, H, n, nkp, w0, w1;
+  int q_tiles;           // 128-query tiles handled here (the tail token of n = 128k+1 is not)
   float scale_log2;
   const uint8_t* mask;
   bf16* o;
@@ -399,6 +400,10 @@ struct AttnPPParams {
 constexpr int kPPSub = 3;                       // 64-key sub-blocks per P buffer (block <= 160 keys)
 constexpr int kPPBuf = kPPSub * kBoxBytes;      // 48 KiB
 
+// kVariant bit 0: streaming softmax (S read twice from TMEM) instead of the register-resident block;
+// bit 1: the row-max exchange synchronises only the two warps sharing a row (named barrier
+// 2 + quarter, 64 threads) instead of all 8 softmax warps.
+template <int kVariant>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -443,7 +448,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
   const uint32_t tmem_base = *tmem_slot;
   // S buffers at columns 0 and 160, O ring at 320 / 384 / 448
 
-  const int T = (p.n + kTile - 1) / kTile;      // query tiles per (b,h); 2 blocks per tile
+  const int T = p.q_tiles;                      // query tiles per (b,h); 2 blocks per tile
   const int inner = p.H * kDh;
 
   if (is_control) {
@@ -531,9 +536,17 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
     __syncwarp();
   } else {
     // ===================== softmax + epilogue warps =====================
+    constexpr bool kResident = (kVariant & 1) == 0;
+    constexpr bool kPairBar = (kVariant & 2) != 0;
     const int half = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    auto row_barrier = [&]() {
+      if constexpr (kPairBar)
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+      else
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     uint32_t g = 0;
     for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
       const int b = bh / p.H, h = bh - b * p.H;
@@ -597,54 +610,100 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
           const uint32_t ts = tmem_base + (g & 1) * 160 + lane_off;
           mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
           tcgen05_fence_after();
-          // The thread's share of the block (<= 5 chunks of 16 keys) stays in registers between
-          // the max pass and the exp pass: one TMEM read + one wait per block.
-          const int nc = ce - cb;
-          uint32_t w[5][16];
-#pragma unroll
-          for (int q = 0; q < 5; ++q)
-            if (q < nc) tmem_ld_32x16(ts + (cb + q) * 16, w[q]);
-          tmem_ld_wait();
-          float m2 = -INFINITY;
-#pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            if (q < nc) {
-              const uint32_t ma = sMul + (k0 + (cb + q) * 16) * 4, aa = sAdd + (k0 + (cb + q) * 16) * 4;
+          float m2 = -INFINITY, sum = 0.f;
+          const uint32_t pbuf = smem_u32(sP) + (g & 1) * kPPBuf;
+          if constexpr (!kResident) {
+            // streaming variant: S is read from TMEM twice, 16 columns at a time
+            for (int c = cb; c < ce; ++c) {
+              uint32_t w[16];
+              tmem_ld_32x16(ts + c * 16, w);
+              tmem_ld_wait();
+              const uint32_t ma = sMul + (k0 + c * 16) * 4, aa = sAdd + (k0 + c * 16) * 4;
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
-                const float t0 = fmaf(__uint_as_float(w[q][i]), mm.x, ad.x);
-                const float t1 = fmaf(__uint_as_float(w[q][i + 1]), mm.y, ad.y);
-                const float t2 = fmaf(__uint_as_float(w[q][i + 2]), mm.z, ad.z);
-                const float t3 = fmaf(__uint_as_float(w[q][i + 3]), mm.w, ad.w);
-                m2 = fmaxf(fmaxf(m2, fmaxf(t0, t1)), fmaxf(t2, t3));
-                w[q][i] = __float_as_uint(t0); w[q][i + 1] = __float_as_uint(t1);
-                w[q][i + 2] = __float_as_uint(t2); w[q][i + 3] = __float_as_uint(t3);
+                m2 = fmaxf(m2, fmaf(__uint_as_float(w[i]), mm.x, ad.x));
+                m2 = fmaxf(m2, fmaf(__uint_as_float(w[i + 1]), mm.y, ad.y));
+                m2 = fmaxf(m2, fmaf(__uint_as_float(w[i + 2]), mm.z, ad.z));
+                m2 = fmaxf(m2, fmaf(__uint_as_float(w[i + 3]), mm.w, ad.w));
               }
             }
-          }
-          sts_f(sMax + (((g & 1) * 2 + half) * 128 + row) * 4, m2);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          m2 = fmaxf(m2, lds_f(sMax + (((g & 1) * 2 + (half ^ 1)) * 128 + row) * 4));
-
-          // P buffer (g&1) was last read by PV(g-2)
-          if (g >= 2) mbar_wait(&o_bar[(g - 2) % 3], ((g - 2) / 3) & 1);
-          float sum = 0.f;
-          const uint32_t pbuf = smem_u32(sP) + (g & 1) * kPPBuf;
+            sts_f(sMax + (((g & 1) * 2 + half) * 128 + row) * 4, m2);
+            row_barrier();
+            m2 = fmaxf(m2, lds_f(sMax + (((g & 1) * 2 + (half ^ 1)) * 128 + row) * 4));
+            if (g >= 2) mbar_wait(&o_bar[(g - 2) % 3], ((g - 2) / 3) & 1);   // P buffer free
+            for (int c = cb; c < ce; ++c) {
+              uint32_t w[16];
+              tmem_ld_32x16(ts + c * 16, w);
+              tmem_ld_wait();
+              const uint32_t ma = sMul + (k0 + c * 16) * 4, aa = sAdd + (k0 + c * 16) * 4;
+              float e[16];
 #pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            if (q < nc) {
-              const int col = (cb + q) * 16;                // column inside the block
+              for (int i = 0; i < 16; i += 4) {
+                const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
+                e[i] = ex2_approx(fmaf(__uint_as_float(w[i]), mm.x, ad.x) - m2);
+                e[i + 1] = ex2_approx(fmaf(__uint_as_float(w[i + 1]), mm.y, ad.y) - m2);
+                e[i + 2] = ex2_approx(fmaf(__uint_as_float(w[i + 2]), mm.z, ad.z) - m2);
+                e[i + 3] = ex2_approx(fmaf(__uint_as_float(w[i + 3]), mm.w, ad.w) - m2);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum += e[i];
+              const int col = c * 16;
               const uint32_t blk = pbuf + (col >> 6) * kBoxBytes;
               const int chunk0 = (col & 63) >> 3;
+              sts_v4(blk + swz128(row, chunk0), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                     pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+              sts_v4(blk + swz128(row, chunk0 + 1), pack_bf16x2(e[8], e[9]),
+                     pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
+            }
+          } else {
+            // The thread's share of the block (<= 5 chunks of 16 keys) stays in registers between
+            // the max pass and the exp pass: one TMEM read + one wait per block.
+            const int nc = ce - cb;
+            uint32_t w[5][16];
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                float e[8];
+            for (int q = 0; q < 5; ++q)
+              if (q < nc) tmem_ld_32x16(ts + (cb + q) * 16, w[q]);
+            tmem_ld_wait();
+            m2 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(__uint_as_float(w[q][hh * 8 + i]) - m2);
-                sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-                sts_v4(blk + swz128(row, chunk0 + hh), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
-                       pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+            for (int q = 0; q < 5; ++q) {
+              if (q < nc) {
+                const uint32_t ma = sMul + (k0 + (cb + q) * 16) * 4, aa = sAdd + (k0 + (cb + q) * 16) * 4;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
+                  const float t0 = fmaf(__uint_as_float(w[q][i]), mm.x, ad.x);
+                  const float t1 = fmaf(__uint_as_float(w[q][i + 1]), mm.y, ad.y);
+                  const float t2 = fmaf(__uint_as_float(w[q][i + 2]), mm.z, ad.z);
+                  const float t3 = fmaf(__uint_as_float(w[q][i + 3]), mm.w, ad.w);
+                  m2 = fmaxf(fmaxf(m2, fmaxf(t0, t1)), fmaxf(t2, t3));
+                  w[q][i] = __float_as_uint(t0); w[q][i + 1] = __float_as_uint(t1);
+                  w[q][i + 2] = __float_as_uint(t2); w[q][i + 3] = __float_as_uint(t3);
+                }
+              }
+            }
+            sts_f(sMax + (((g & 1) * 2 + half) * 128 + row) * 4, m2);
+            row_barrier();
+            m2 = fmaxf(m2, lds_f(sMax + (((g & 1) * 2 + (half ^ 1)) * 128 + row) * 4));
+
+            // P buffer (g&1) was last read by PV(g-2)
+            if (g >= 2) mbar_wait(&o_bar[(g - 2) % 3], ((g - 2) / 3) & 1);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              if (q < nc) {
+                const int col = (cb + q) * 16;                // column inside the block
+                const uint32_t blk = pbuf + (col >> 6) * kBoxBytes;
+                const int chunk0 = (col & 63) >> 3;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  float e[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) e[i] = ex2_approx(__uint_as_float(w[q][hh * 8 + i]) - m2);
+                  sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                  sts_v4(blk + swz128(row, chunk0 + hh), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                         pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+                }
               }
             }
           }
@@ -673,25 +732,45 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
   }
 }
 
-static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, cudaStream_t stream) {
+int launch_attn_fwd_tail(const void* qkv, long long ld, const uint8_t* mask, void* o, long long ldo,
+                         float* lse, int B, int H, int n, float scale_log2, cudaStream_t stream);
+
+static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, bool tail,
+                              cudaStream_t stream) {
   AttnPPParams p;
   p.B = q.B; p.H = q.H; p.n = q.n; p.nkp = q.nkp;
+  p.q_tiles = tail ? (q.n - 1) / kTile : (q.n + kTile - 1) / kTile;
   p.w0 = ((q.nkp / 2) + 15) / 16 * 16;
   p.w1 = q.nkp - p.w0;
   p.scale_log2 = q.scale_log2; p.mask = q.mask; p.o = q.o; p.ldo = q.ldo; p.lse = q.lse;
   const int nkb = (q.n + kTile - 1) / kTile;
   const int smem = (1 + 2 * nkb) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 4 * 128 * 4 +
                    8 * 128 * 4;
+  static const int variant = [] {
+    const char* e = getenv("XCLIP_ATTN_PP_VARIANT");
+    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+  }();
   static bool configured = false;
   if (!configured) {
-    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (1 + 6) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 +
-                                        4 * 128 * 4 + 8 * 128 * 4));
+    const int max_smem = (1 + 6) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 4 * 128 * 4 + 8 * 128 * 4;
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<0>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<1>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   long long grid = num_sms();
   if (grid > (long long)q.B * q.H) grid = (long long)q.B * q.H;
-  attn_fwd_pp_kernel<<<(int)grid, kAttnThreads, smem, stream>>>(tm, p);
+  switch (variant) {
+    case 1: attn_fwd_pp_kernel<1><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
+    case 2: attn_fwd_pp_kernel<2><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
+    case 3: attn_fwd_pp_kernel<3><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
+    default: attn_fwd_pp_kernel<0><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
+  }
   XCLIP_LAUNCH_CHECK("attn_fwd_pp_kernel");
   return XCLIP_OK;
 }
@@ -730,8 +809,14 @@ extern "C" int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
   if (rc) return rc;
 
   static const bool use_pp = [] { const char* e = getenv("XCLIP_ATTN_PP"); return !(e && e[0] == '0'); }();
-  if (use_pp && n > kTile && p.nkp - ((p.nkp / 2) + 15) / 16 * 16 >= 16)
-    return launch_attn_fwd_pp(tm, p, reinterpret_cast<cudaStream_t>(stream));
+  if (use_pp && n > kTile && p.nkp - ((p.nkp / 2) + 15) / 16 * 16 >= 16) {
+    // n = 128k + 1 (a CLS token on top of whole tiles): the last query is done on CUDA cores
+    const bool tail = attn_tail_enabled() && n % kTile == 1;
+    rc = launch_attn_fwd_pp(tm, p, tail, reinterpret_cast<cudaStream_t>(stream));
+    if (rc || !tail) return rc;
+    return launch_attn_fwd_tail(qkv, ld_qkv, key_mask, o, ldo, lse, B, heads, n, p.scale_log2,
+                                reinterpret_cast<cudaStream_t>(stream));
+  }
 
   const int nkb = (n + kTile - 1) / kTile;
   const int npb = (p.nkp + 63) / 64;

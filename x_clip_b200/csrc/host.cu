@@ -1,6 +1,8 @@
 // Library-level C-ABI entry points and host helpers (errors, TMA descriptor encoding).
 #include "host.h"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -65,6 +67,14 @@ static int do_init() {
 }
 
 int num_sms() { return g_sms; }
+
+bool attn_tail_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("XCLIP_ATTN_TAIL");
+    return e && e[0] == '1';   // opt-in until the path has been validated on hardware
+  }();
+  return on;
+}
 
 int encode_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
                    uint64_t outer_stride_elems, uint32_t box_inner, uint32_t box_outer) {

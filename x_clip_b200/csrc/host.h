@@ -18,6 +18,10 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 
+// XCLIP_ATTN_TAIL=1 enables the CUDA-core tail-token path of the attention kernels (n = 128k+1);
+// off by default: it has not been validated on a B200 yet
+bool attn_tail_enabled();
+
 // counts kernel launches made by this library (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 
