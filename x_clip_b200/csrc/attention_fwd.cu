@@ -732,6 +732,311 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warpgroup ping-pong variant (XCLIP_ATTN_PP_VARIANT=4, experimental - see DESIGN.md section 9).
+// Same TMEM / smem plan and issue-thread schedule as attn_fwd_pp_kernel, different softmax
+// mapping: a row is owned by ONE thread per key block - warpgroup 0 (warps 0-3) takes the first
+// key block of every tile, warpgroup 1 the second - so there is no row-max exchange and no
+// CTA-wide barrier in the loop; the two warpgroups only meet in the epilogue, through a ring of
+// per-block (max, sum) pairs in shared memory.  Because a warpgroup no longer implies that the
+// other one is past its deferred epilogue, the O ring gets an explicit "epilogue done" barrier
+// per tile (e_bar, 8 arrivals) that the issue thread checks before a PV overwrites a ring slot.
+template <int N>
+__device__ __forceinline__ float wg_pass_max(const uint32_t (&w)[N], uint32_t ma, uint32_t aa, float m) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
+    const float t0 = fmaf(__uint_as_float(w[i]), mm.x, ad.x);
+    const float t1 = fmaf(__uint_as_float(w[i + 1]), mm.y, ad.y);
+    const float t2 = fmaf(__uint_as_float(w[i + 2]), mm.z, ad.z);
+    const float t3 = fmaf(__uint_as_float(w[i + 3]), mm.w, ad.w);
+    m = fmaxf(fmaxf(m, fmaxf(t0, t1)), fmaxf(t2, t3));
+  }
+  return m;
+}
+// exp2 of N (16 or 32) columns starting at block column `col`, bf16 P into the swizzled buffer
+template <int N>
+__device__ __forceinline__ float wg_pass_exp(const uint32_t (&w)[N], uint32_t ma, uint32_t aa, float m,
+                                             uint32_t pbuf, int row, int col) {
+  float sum = 0.f;
+  const uint32_t blk = pbuf + (col >> 6) * kBoxBytes;
+  const int chunk0 = (col & 63) >> 3;
+#pragma unroll
+  for (int i = 0; i < N; i += 8) {
+    const float4 m0 = lds_f4(ma + i * 4), a0 = lds_f4(aa + i * 4);
+    const float4 m1 = lds_f4(ma + (i + 4) * 4), a1 = lds_f4(aa + (i + 4) * 4);
+    float e[8];
+    e[0] = ex2_approx(fmaf(__uint_as_float(w[i]), m0.x, a0.x) - m);
+    e[1] = ex2_approx(fmaf(__uint_as_float(w[i + 1]), m0.y, a0.y) - m);
+    e[2] = ex2_approx(fmaf(__uint_as_float(w[i + 2]), m0.z, a0.z) - m);
+    e[3] = ex2_approx(fmaf(__uint_as_float(w[i + 3]), m0.w, a0.w) - m);
+    e[4] = ex2_approx(fmaf(__uint_as_float(w[i + 4]), m1.x, a1.x) - m);
+    e[5] = ex2_approx(fmaf(__uint_as_float(w[i + 5]), m1.y, a1.y) - m);
+    e[6] = ex2_approx(fmaf(__uint_as_float(w[i + 6]), m1.z, a1.z) - m);
+    e[7] = ex2_approx(fmaf(__uint_as_float(w[i + 7]), m1.w, a1.w) - m);
+    sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+    sts_v4(blk + swz128(row, chunk0 + (i >> 3)), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+           pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nkb = (p.n + kTile - 1) / kTile;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kBoxBytes;
+  uint8_t* sV = sK + nkb * kBoxBytes;
+  uint8_t* sP = sV + nkb * kBoxBytes;           // 2 buffers (one per warpgroup / key block)
+  uint8_t* tail = sP + 2 * kPPBuf;
+  uint64_t* k_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* q_bar = k_bar + 1;
+  uint64_t* s_bar = k_bar + 2;     // [2]
+  uint64_t* p_bar = k_bar + 4;     // [2], 4 arrivals each (the warps of one warpgroup)
+  uint64_t* o_bar = k_bar + 6;     // [3]
+  uint64_t* v_bar = k_bar + 9;
+  uint64_t* e_bar = k_bar + 10;    // [2] by tile parity, 8 arrivals: epilogue of the tile done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_bar + 12);
+  const uint32_t sMul = smem_u32(tail + 128);           // [384] f32
+  const uint32_t sAdd = sMul + 384 * 4;                 // [384] f32
+  const uint32_t sStatM = sAdd + 384 * 4;               // [8 block slots][128] f32 block max
+  const uint32_t sStatL = sStatM + 8 * 128 * 4;         // [8 block slots][128] f32 block sum
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool is_control = warp == kAttnComputeWarps;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    mbar_init(k_bar, 1);
+    mbar_init(v_bar, 1);
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_bar[i], 1);
+      mbar_init(&p_bar[i], kAttnComputeWarps / 2);
+      mbar_init(&e_bar[i], kAttnComputeWarps);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&o_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (is_control) {
+    if (lane == 0) tma_prefetch_desc(&tm_qkv);
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = p.q_tiles;
+  const int inner = p.H * kDh;
+
+  if (is_control) {
+    if (lane == 0) {
+      const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 0, 1024);
+      const uint64_t desc_k = make_smem_desc(smem_u32(sK), 0, 1024);
+      const uint64_t desc_v = make_smem_desc(smem_u32(sV), 8192, 1024);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, kMajorK, kMajorMN);
+      const uint32_t idesc_s0 = make_idesc_bf16(kTile, p.w0, kMajorK, kMajorK);
+      const uint32_t idesc_s1 = make_idesc_bf16(kTile, p.w1, kMajorK, kMajorK);
+      auto issue_pv = [&](uint32_t gb) {        // O[gb % 3] = P(gb) V_blk(gb)
+        const int kb = gb & 1;
+        const int k0 = kb ? p.w0 : 0, W = kb ? p.w1 : p.w0;
+        mbar_wait(&p_bar[gb & 1], (gb >> 1) & 1);
+        if (gb >= 3) {                           // ring slot gb%3 held block gb-3: its tile's
+          const uint32_t te = (gb - 3) >> 1;     // epilogue must have read it
+          mbar_wait(&e_bar[te & 1], (te >> 1) & 1);
+        }
+        tcgen05_fence_after();
+        const uint64_t pd = make_smem_desc(smem_u32(sP) + (gb & 1) * kPPBuf, 0, 1024);
+        const uint64_t vd = desc_v + ((k0 * 128) >> 4);
+        const uint32_t td = tmem_base + 320 + (gb % 3) * kDh;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (k < W / 16)
+            umma_bf16(td, pd + ((k >> 2) * (kBoxBytes >> 4) + (k & 3) * 2), vd + k * 128, idesc_pv,
+                      k > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_bar[gb % 3]);
+      };
+      auto load_kq = [&](int bh2) {
+        const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+        mbar_arrive_expect_tx(k_bar, nkb * kBoxBytes);
+        for (int i = 0; i < nkb; ++i)
+          tma_load_3d(sK + i * kBoxBytes, &tm_qkv, k_bar, inner + h2 * kDh, i * kTile, b2);
+        mbar_arrive_expect_tx(q_bar, kBoxBytes);
+        tma_load_3d(sQ, &tm_qkv, q_bar, h2 * kDh, 0, b2);
+      };
+      auto load_v = [&](int bh2) {
+        const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+        mbar_arrive_expect_tx(v_bar, nkb * kBoxBytes);
+        for (int i = 0; i < nkb; ++i)
+          tma_load_3d(sV + i * kBoxBytes, &tm_qkv, v_bar, 2 * inner + h2 * kDh, i * kTile, b2);
+      };
+      uint32_t g = 0, tt = 0, kvc = 0;
+      const int total = p.B * p.H;
+      if ((int)blockIdx.x < total) { load_kq(blockIdx.x); load_v(blockIdx.x); }
+      for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++kvc) {
+        const int b = bh / p.H, h = bh - b * p.H;
+        const int bh_next = bh + gridDim.x;
+        mbar_wait(k_bar, kvc & 1);
+        for (int t = 0; t < T; ++t) {
+          for (int kb = 0; kb < 2; ++kb, ++g) {
+            const int k0 = kb ? p.w0 : 0;
+            if (kb == 0) { mbar_wait(q_bar, tt & 1); ++tt; }
+            if (g >= 2) mbar_wait(&p_bar[g & 1], ((g - 2) >> 1) & 1);   // S[g&1] consumed
+            tcgen05_fence_after();
+            {
+              const uint64_t kd = desc_k + ((k0 * 128) >> 4);
+              const uint32_t ts = tmem_base + (g & 1) * 160;
+              const uint32_t idesc = kb ? idesc_s1 : idesc_s0;
+#pragma unroll
+              for (int k = 0; k < kDh / 16; ++k)
+                umma_bf16(ts, desc_q + 2 * k, kd + 2 * k, idesc, k > 0 ? 1u : 0u);
+              umma_commit(&s_bar[g & 1]);
+            }
+            if (kb == 1) {
+              if (t + 1 < T) {
+                mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+                mbar_arrive_expect_tx(q_bar, kBoxBytes);
+                tma_load_3d(sQ, &tm_qkv, q_bar, h * kDh, (t + 1) * kTile, b);
+              } else if (bh_next < total) {
+                mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+                load_kq(bh_next);
+              }
+            }
+            if (t == 0 && kb == 1) mbar_wait(v_bar, kvc & 1);
+            if (!(t == 0 && kb == 0)) issue_pv(g - 1);
+          }
+        }
+        issue_pv(g - 1);
+        mbar_wait(&o_bar[(g - 1) % 3], ((g - 1) / 3) & 1);
+        if (bh_next < total) load_v(bh_next);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue warps =====================
+    const int wg = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int k0 = wg ? p.w0 : 0, W = wg ? p.w1 : p.w0;   // this warpgroup's key block
+    const uint32_t ts = tmem_base + wg * 160 + lane_off;
+    const uint32_t pbuf = smem_u32(sP) + wg * kPPBuf;
+    const uint32_t ma0 = sMul + k0 * 4, aa0 = sAdd + k0 * 4;
+    uint32_t gt = 0;                                       // global tile counter of this CTA
+    for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
+      const int b = bh / p.H, h = bh - b * p.H;
+      for (int j = threadIdx.x; j < 384; j += kAttnComputeWarps * 32) {
+        float mul = 0.f, add = -INFINITY;
+        if (j < p.n) {
+          const bool keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
+          mul = keep ? p.scale_log2 : 0.f;
+          add = keep ? 0.f : -FLT_MAX;
+        }
+        sts_f(sMul + j * 4, mul);
+        sts_f(sAdd + j * 4, add);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+
+      auto epilogue = [&](int t, uint32_t gtile) {
+        const uint32_t g0 = 2 * gtile, g1 = g0 + 1;
+        mbar_wait(&o_bar[g0 % 3], (g0 / 3) & 1);
+        mbar_wait(&o_bar[g1 % 3], (g1 / 3) & 1);
+        tcgen05_fence_after();
+        const int q_idx = t * kTile + row;
+        const float m0 = lds_f(sStatM + ((g0 & 7) * 128 + row) * 4);
+        const float l0 = lds_f(sStatL + ((g0 & 7) * 128 + row) * 4);
+        const float m1 = lds_f(sStatM + ((g1 & 7) * 128 + row) * 4);
+        const float l1 = lds_f(sStatL + ((g1 & 7) * 128 + row) * 4);
+        const float m = fmaxf(m0, m1);
+        const float a0 = ex2_approx(m0 - m), a1 = ex2_approx(m1 - m);
+        const float L = a0 * l0 + a1 * l1;
+        const float inv = 1.f / L;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(tmem_base + 320 + (g0 % 3) * kDh + lane_off + wg * 32, v0);
+        tmem_ld_32x32(tmem_base + 320 + (g1 % 3) * kDh + lane_off + wg * 32, v1);
+        tmem_ld_wait();
+        // both O buffers are in registers: release the ring slots before the global stores
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&e_bar[gtile & 1]);
+        if (q_idx < p.n) {
+          if (wg == 0) p.lse[((long long)b * p.H + h) * p.n + q_idx] = m + log2f(L);
+          bf16* dst = p.o + ((long long)b * p.n + q_idx) * p.ldo + h * kDh + wg * 32;
+          const float c0 = a0 * inv, c1 = a1 * inv;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              f[e] = __uint_as_float(v0[i + e]) * c0 + __uint_as_float(v1[i + e]) * c1;
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(dst + i) = o;
+          }
+        }
+      };
+
+      for (int t = 0; t < T; ++t, ++gt) {
+        const uint32_t gb = 2 * gt + wg;                   // this warpgroup's block of tile t
+        const bool warp_alive = t * kTile + quarter * 32 < p.n;
+        mbar_wait(&s_bar[wg], gt & 1);
+        tcgen05_fence_after();
+        float m2 = -INFINITY, sum = 0.f;
+        if (warp_alive) {
+          for (int c = 0; c < W; c += 32) {
+            if (c + 32 <= W) {
+              uint32_t w[32];
+              tmem_ld_32x32(ts + c, w);
+              tmem_ld_wait();
+              m2 = wg_pass_max<32>(w, ma0 + c * 4, aa0 + c * 4, m2);
+            } else {
+              uint32_t w[16];
+              tmem_ld_32x16(ts + c, w);
+              tmem_ld_wait();
+              m2 = wg_pass_max<16>(w, ma0 + c * 4, aa0 + c * 4, m2);
+            }
+          }
+        }
+        // this warpgroup's P buffer was last read by PV(gb-2)
+        if (gb >= 2) mbar_wait(&o_bar[(gb - 2) % 3], ((gb - 2) / 3) & 1);
+        if (warp_alive) {
+          for (int c = 0; c < W; c += 32) {
+            if (c + 32 <= W) {
+              uint32_t w[32];
+              tmem_ld_32x32(ts + c, w);
+              tmem_ld_wait();
+              sum += wg_pass_exp<32>(w, ma0 + c * 4, aa0 + c * 4, m2, pbuf, row, c);
+            } else {
+              uint32_t w[16];
+              tmem_ld_32x16(ts + c, w);
+              tmem_ld_wait();
+              sum += wg_pass_exp<16>(w, ma0 + c * 4, aa0 + c * 4, m2, pbuf, row, c);
+            }
+          }
+        }
+        sts_f(sStatM + ((gb & 7) * 128 + row) * 4, m2);
+        sts_f(sStatL + ((gb & 7) * 128 + row) * 4, sum);
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_bar[wg]);
+        if (t > 0) epilogue(t - 1, gt - 1);                // deferred behind this tile's softmax
+      }
+      epilogue(T - 1, gt - 1);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (is_control) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 int launch_attn_fwd_tail(const void* qkv, long long ld, const uint8_t* mask, void* o, long long ldo,
                          float* lse, int B, int H, int n, float scale_log2, cudaStream_t stream);
 
@@ -744,15 +1049,16 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
   p.w1 = q.nkp - p.w0;
   p.scale_log2 = q.scale_log2; p.mask = q.mask; p.o = q.o; p.ldo = q.ldo; p.lse = q.lse;
   const int nkb = (q.n + kTile - 1) / kTile;
-  const int smem = (1 + 2 * nkb) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 4 * 128 * 4 +
-                   8 * 128 * 4;
   static const int variant = [] {
     const char* e = getenv("XCLIP_ATTN_PP_VARIANT");
-    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+    return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;
   }();
+  // barriers + mask tables + per-row exchange buffers (variant 4: 2 x 8-slot statistics ring)
+  const int tail_bytes = 128 + 2 * 384 * 4 + (variant == 4 ? 16 * 128 * 4 : (4 + 8) * 128 * 4);
+  const int smem = (1 + 2 * nkb) * kBoxBytes + 2 * kPPBuf + tail_bytes;
   static bool configured = false;
   if (!configured) {
-    const int max_smem = (1 + 6) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 4 * 128 * 4 + 8 * 128 * 4;
+    const int max_smem = (1 + 6) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 16 * 128 * 4;
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<0>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<1>,
@@ -761,6 +1067,8 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<3>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    max_smem));
     configured = true;
   }
   long long grid = num_sms();
@@ -769,6 +1077,7 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
     case 1: attn_fwd_pp_kernel<1><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
     case 2: attn_fwd_pp_kernel<2><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
     case 3: attn_fwd_pp_kernel<3><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
+    case 4: attn_fwd_wg_kernel<<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
     default: attn_fwd_pp_kernel<0><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
   }
   XCLIP_LAUNCH_CHECK("attn_fwd_pp_kernel");
