@@ -63,6 +63,10 @@ def parse():
                          "projections (cfg5); filip: use_all_token_embeds (cfg4)")
     ap.add_argument("--microbatch", type=int, default=0,
                     help="encoder micro-batch (GradCache-style step) - lets --batch 4096 fit one GPU")
+    ap.add_argument("--grad-sync", action="store_true",
+                    help="N>1: also all-reduce the weight gradients inside the timed step "
+                         "(x_clip_b200.distributed.GradSync, buckets overlapped with backward); the "
+                         "reference leaves this to the user's DDP wrapper, so it is off by default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",
@@ -241,11 +245,18 @@ def main():
         dev_img = host[0][1].to(dev)
         h2d_bytes = host[0][0].numel() * 8 + host[0][1].numel() * 4
 
+    grad_sync = None
+    if args.grad_sync and world > 1:
+        from x_clip_b200.distributed import GradSync
+        grad_sync = GradSync(clip)
+
     def step(text, image):
         for p in params:
             p.grad = None
         loss = clip(text, image, return_loss=True)
         loss.backward()
+        if grad_sync is not None:
+            grad_sync.finish()
         return loss
 
     def barrier():
@@ -393,7 +404,7 @@ def main():
                        "plain InfoNCE", {"nce": "plain InfoNCE", "dcl_extra": "DCL + extra latent projection",
                                          "filip": "FILIP (use_all_token_embeds)"}[args.loss]) + (f", encoder micro-batch {args.microbatch} "
                    "(two-pass GradCache step: +1 encoder forward)" if args.microbatch else ""),
-                   "global_batch": Bg, "parallelism": f"dp{world}",
+                   "global_batch": Bg, "parallelism": f"dp{world}" + ("+grad-allreduce" if args.grad_sync and world > 1 else ""),
                    "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed",
                    "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks",
                    "loss": round(last_loss, 5)},

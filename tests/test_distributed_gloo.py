@@ -102,3 +102,75 @@ def test_reduce_scatter_rows_two_ranks():
     for p in procs:
         p.join(timeout=30)
     assert all(ok for _, ok in res)
+
+
+def _gs_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from x_clip_b200 import distributed as D
+    torch.manual_seed(0)                                      # identical weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.GELU(), torch.nn.Linear(16, 16),
+                              torch.nn.GELU(), torch.nn.Linear(16, 3))
+    frozen = torch.nn.Linear(3, 3)                            # never receives a gradient
+    mod = torch.nn.ModuleList([net, frozen])
+    import copy
+    ref_net = copy.deepcopy(net)                              # hook-free twin for the expected values
+    sync = D.GradSync(mod, bucket_bytes=600)                  # several small buckets
+    nb = len(sync._buckets)
+    errs = []
+    for step in range(2):                                     # re-arming across steps
+        data = [torch.randn(5, 6, generator=torch.Generator().manual_seed(10 * step + r))
+                for r in range(world)]
+        mod.zero_grad(set_to_none=True)
+        net(data[rank]).square().sum().backward()
+        sync.finish()
+        got = [p.grad.clone() for p in net.parameters()]
+        want = [torch.zeros_like(p) for p in net.parameters()]
+        for r in range(world):                                # single-process reference: mean over ranks
+            ref_net.zero_grad(set_to_none=True)
+            ref_net(data[r]).square().sum().backward()
+            for w, p in zip(want, ref_net.parameters()):
+                w += p.grad / world
+        errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
+    unused_ok = all(p.grad is None for p in frozen.parameters())
+    q.put((rank, nb, max(errs), unused_ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_sync_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gs_worker, args=(r, world, 29735, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = []
+    import queue as _q, time as _t
+    t0 = _t.time()
+    while len(res) < world and _t.time() - t0 < 240:
+        try:
+            res.append(q.get(timeout=2))
+        except _q.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    for p in procs:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    assert len(res) == world, "a rank died (see its traceback above)"
+    for rank, nb, err, unused_ok in res:
+        assert nb >= 3, "the test is meant to exercise several buckets"
+        assert err < 1e-6, f"rank {rank}: synced gradients differ from the mean of the ranks' gradients by {err}"
+        assert unused_ok
+
+
+def test_grad_sync_single_rank_is_noop():
+    from x_clip_b200 import distributed as D
+    lin = torch.nn.Linear(4, 4)
+    sync = D.GradSync(lin)
+    lin(torch.randn(2, 4)).sum().backward()
+    g = lin.weight.grad.clone()
+    sync.finish()
+    assert torch.equal(lin.weight.grad, g)

@@ -69,3 +69,116 @@ def reduce_scatter_rows(t: torch.Tensor) -> torch.Tensor:
     out = torch.empty((rows,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
     dist.reduce_scatter_tensor(out, t)
     return out
+
+
+class GradSync:
+    """Bucketed all-reduce of parameter gradients, launched from inside backward.
+
+    The reference leaves data-parallel weight synchronisation to the user's DDP wrapper
+    (its README trains single-GPU).  This is the minimal equivalent
+    for the CLIP module of this package: parameters are grouped into buckets in REVERSE
+    registration order (late layers finish their backward first); a post-accumulate-grad hook
+    counts arrivals and, once a bucket is complete, flattens it and starts an asynchronous
+    all-reduce - on NCCL that runs on the communicator's own stream, so it overlaps the rest of
+    backward.  `finish()` (call it after `loss.backward()`, before the optimizer) waits for the
+    collectives, divides by the world size (`average=True`, the DDP convention) and scatters
+    the result back into `p.grad`.
+
+    Every rank must build the same autograd graph (same parameters receive gradients), which
+    holds for `CLIP.forward(..., return_loss=True)` with equal flags on all ranks.  Parameters
+    that received no gradient (frozen encoder, unused extra projections) are skipped by all
+    ranks alike.  With a single rank everything is a no-op.  For gradient accumulation wrap the
+    non-final backward passes in `with sync.no_sync():` (as with DDP) - a bucket is reduced once,
+    when its last gradient of the pass arrives.
+    """
+
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 64 << 20, average: bool = True,
+                 comm_dtype: torch.dtype | None = None, process_group=None):
+        self.world = world()[1]
+        self.average = average
+        self.comm_dtype = comm_dtype
+        self.group = process_group
+        self.enabled = True
+        self._buckets: List[dict] = []
+        self._bucket_of = {}
+        self._handles = []
+        if self.world == 1:
+            return
+        params = [p for p in module.parameters() if p.requires_grad]
+        cur, cur_bytes = [], 0
+        for p in reversed(params):
+            nbytes = p.numel() * p.element_size()
+            if cur and (cur_bytes + nbytes > bucket_bytes or p.dtype != cur[0].dtype
+                        or p.device != cur[0].device):
+                self._add_bucket(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._add_bucket(cur)
+        for p in params:
+            self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _add_bucket(self, params):
+        b = {"params": list(params), "arrived": 0, "work": None, "flat": None, "members": None}
+        for p in params:
+            self._bucket_of[p] = b
+        self._buckets.append(b)
+
+    def no_sync(self):
+        """Context manager: backward passes inside it accumulate locally (no collectives)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def _cm():
+            prev, self.enabled = self.enabled, False
+            try:
+                yield
+            finally:
+                self.enabled = prev
+        return _cm()
+
+    def _on_grad(self, p):
+        if not self.enabled:
+            return
+        b = self._bucket_of[p]
+        b["arrived"] += 1
+        if b["arrived"] == len(b["params"]):
+            self._launch(b)
+
+    def _launch(self, b):
+        members = [p for p in b["params"] if p.grad is not None]
+        b["members"] = members
+        if not members:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in members])
+        if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
+            flat = flat.to(self.comm_dtype)
+        b["flat"] = flat
+        b["work"] = dist.all_reduce(flat, group=self.group, async_op=True)
+
+    def finish(self):
+        """Wait for every bucket, write the reduced gradients back, re-arm for the next step."""
+        if self.world == 1:
+            return
+        for b in self._buckets:
+            if b["members"] is None:          # some parameter of the bucket got no gradient
+                self._launch(b)
+        for b in self._buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+                flat = b["flat"]
+                off = 0
+                for p in b["members"]:
+                    n = p.numel()
+                    red = flat[off:off + n].view_as(p.grad).to(p.grad.dtype)
+                    if self.average:
+                        red = red / self.world
+                    p.grad.copy_(red)
+                    off += n
+            b["arrived"], b["work"], b["flat"], b["members"] = 0, None, None, None
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
