@@ -80,6 +80,14 @@ __device__ __forceinline__ float lds_f(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_f(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -733,47 +741,69 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warpgroup ping-pong variant (XCLIP_ATTN_PP_VARIANT=4, experimental - see DESIGN.md section 9).
+// Warpgroup ping-pong variants (XCLIP_ATTN_PP_VARIANT=4..7, experimental - DESIGN.md section 9).
 // Same TMEM / smem plan and issue-thread schedule as attn_fwd_pp_kernel, different softmax
-// mapping: a row is owned by ONE thread per key block - warpgroup 0 (warps 0-3) takes the first
-// key block of every tile, warpgroup 1 the second - so there is no row-max exchange and no
-// CTA-wide barrier in the loop; the two warpgroups only meet in the epilogue, through a ring of
-// per-block (max, sum) pairs in shared memory.  Because a warpgroup no longer implies that the
-// other one is past its deferred epilogue, the O ring gets an explicit "epilogue done" barrier
-// per tile (e_bar, 8 arrivals) that the issue thread checks before a PV overwrites a ring slot.
-template <int N>
-__device__ __forceinline__ float wg_pass_max(const uint32_t (&w)[N], uint32_t ma, uint32_t aa, float m) {
+// mapping: the two key blocks of a tile are processed CONCURRENTLY by different warpgroups
+// (block 0 <-> S buffer 0, block 1 <-> S buffer 1), so there is no CTA-wide barrier in the loop and
+// the warpgroups only meet in the epilogue through a ring of per-block (max, sum) statistics.
+//   kHalves = 1:  8 softmax warps; a row of a block is owned by ONE thread (no max exchange).
+//   kHalves = 2: 16 softmax warps (4 per scheduler); two warps share a row of a block (column
+//                halves) and exchange the row max through a 64-thread named barrier.
+//   kFast: 16-column chunks without masked / padded keys skip the mask tables:
+//          p = 2^(s*c - m) is one FFMA + EX2, the max pass works on raw scores.
+// Because a warpgroup no longer implies that the others are past their deferred epilogue, the O
+// ring gets an explicit "epilogue done" barrier per tile (e_bar) that the issue thread checks
+// before a PV overwrites a ring slot.
+template <int N, bool kFastPath>
+__device__ __forceinline__ void wg_pass_max(const uint32_t (&w)[N], uint32_t ma, uint32_t aa,
+                                            float& m_scaled, float& m_raw) {
+  if constexpr (kFastPath) {
+    float m = m_raw;
 #pragma unroll
-  for (int i = 0; i < N; i += 4) {
-    const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
-    const float t0 = fmaf(__uint_as_float(w[i]), mm.x, ad.x);
-    const float t1 = fmaf(__uint_as_float(w[i + 1]), mm.y, ad.y);
-    const float t2 = fmaf(__uint_as_float(w[i + 2]), mm.z, ad.z);
-    const float t3 = fmaf(__uint_as_float(w[i + 3]), mm.w, ad.w);
-    m = fmaxf(fmaxf(m, fmaxf(t0, t1)), fmaxf(t2, t3));
+    for (int i = 0; i < N; i += 4)
+      m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(w[i]), __uint_as_float(w[i + 1]))),
+                fmaxf(__uint_as_float(w[i + 2]), __uint_as_float(w[i + 3])));
+    m_raw = m;
+  } else {
+    float m = m_scaled;
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      const float4 mm = lds_f4(ma + i * 4), ad = lds_f4(aa + i * 4);
+      const float t0 = fmaf(__uint_as_float(w[i]), mm.x, ad.x);
+      const float t1 = fmaf(__uint_as_float(w[i + 1]), mm.y, ad.y);
+      const float t2 = fmaf(__uint_as_float(w[i + 2]), mm.z, ad.z);
+      const float t3 = fmaf(__uint_as_float(w[i + 3]), mm.w, ad.w);
+      m = fmaxf(fmaxf(m, fmaxf(t0, t1)), fmaxf(t2, t3));
+    }
+    m_scaled = m;
   }
-  return m;
 }
 // exp2 of N (16 or 32) columns starting at block column `col`, bf16 P into the swizzled buffer
-template <int N>
+template <int N, bool kFastPath>
 __device__ __forceinline__ float wg_pass_exp(const uint32_t (&w)[N], uint32_t ma, uint32_t aa, float m,
-                                             uint32_t pbuf, int row, int col) {
+                                             float c, uint32_t pbuf, int row, int col) {
   float sum = 0.f;
   const uint32_t blk = pbuf + (col >> 6) * kBoxBytes;
   const int chunk0 = (col & 63) >> 3;
+  const float neg_m = -m;
 #pragma unroll
   for (int i = 0; i < N; i += 8) {
-    const float4 m0 = lds_f4(ma + i * 4), a0 = lds_f4(aa + i * 4);
-    const float4 m1 = lds_f4(ma + (i + 4) * 4), a1 = lds_f4(aa + (i + 4) * 4);
     float e[8];
-    e[0] = ex2_approx(fmaf(__uint_as_float(w[i]), m0.x, a0.x) - m);
-    e[1] = ex2_approx(fmaf(__uint_as_float(w[i + 1]), m0.y, a0.y) - m);
-    e[2] = ex2_approx(fmaf(__uint_as_float(w[i + 2]), m0.z, a0.z) - m);
-    e[3] = ex2_approx(fmaf(__uint_as_float(w[i + 3]), m0.w, a0.w) - m);
-    e[4] = ex2_approx(fmaf(__uint_as_float(w[i + 4]), m1.x, a1.x) - m);
-    e[5] = ex2_approx(fmaf(__uint_as_float(w[i + 5]), m1.y, a1.y) - m);
-    e[6] = ex2_approx(fmaf(__uint_as_float(w[i + 6]), m1.z, a1.z) - m);
-    e[7] = ex2_approx(fmaf(__uint_as_float(w[i + 7]), m1.w, a1.w) - m);
+    if constexpr (kFastPath) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) e[u] = ex2_approx(fmaf(__uint_as_float(w[i + u]), c, neg_m));
+    } else {
+      const float4 m0 = lds_f4(ma + i * 4), a0 = lds_f4(aa + i * 4);
+      const float4 m1 = lds_f4(ma + (i + 4) * 4), a1 = lds_f4(aa + (i + 4) * 4);
+      e[0] = ex2_approx(fmaf(__uint_as_float(w[i]), m0.x, a0.x) - m);
+      e[1] = ex2_approx(fmaf(__uint_as_float(w[i + 1]), m0.y, a0.y) - m);
+      e[2] = ex2_approx(fmaf(__uint_as_float(w[i + 2]), m0.z, a0.z) - m);
+      e[3] = ex2_approx(fmaf(__uint_as_float(w[i + 3]), m0.w, a0.w) - m);
+      e[4] = ex2_approx(fmaf(__uint_as_float(w[i + 4]), m1.x, a1.x) - m);
+      e[5] = ex2_approx(fmaf(__uint_as_float(w[i + 5]), m1.y, a1.y) - m);
+      e[6] = ex2_approx(fmaf(__uint_as_float(w[i + 6]), m1.z, a1.z) - m);
+      e[7] = ex2_approx(fmaf(__uint_as_float(w[i + 7]), m1.w, a1.w) - m);
+    }
     sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
     sts_v4(blk + swz128(row, chunk0 + (i >> 3)), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
            pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
@@ -781,31 +811,39 @@ __device__ __forceinline__ float wg_pass_exp(const uint32_t (&w)[N], uint32_t ma
   return sum;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+constexpr int kWgTableCols = 320;   // n <= 320 -> nkp <= 320
+constexpr int kWgTailBytes = 128 + 2 * kWgTableCols * 4 + 128 + 8 * 128 * 4 + 16 * 128 * 4 + 8 * 128 * 4;
+
+template <int kHalves, bool kFast>
+__global__ void __launch_bounds__((8 * kHalves + 1) * 32, 1)
 attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParams p) {
+  constexpr int kWarps = 8 * kHalves;            // softmax warps; warp kWarps is the control warp
+  constexpr int kOCols = 64 / (2 * kHalves);     // O columns per thread in the epilogue
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nkb = (p.n + kTile - 1) / kTile;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kBoxBytes;
   uint8_t* sV = sK + nkb * kBoxBytes;
-  uint8_t* sP = sV + nkb * kBoxBytes;           // 2 buffers (one per warpgroup / key block)
+  uint8_t* sP = sV + nkb * kBoxBytes;           // 2 buffers (one per key block)
   uint8_t* tail = sP + 2 * kPPBuf;
   uint64_t* k_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* q_bar = k_bar + 1;
   uint64_t* s_bar = k_bar + 2;     // [2]
-  uint64_t* p_bar = k_bar + 4;     // [2], 4 arrivals each (the warps of one warpgroup)
+  uint64_t* p_bar = k_bar + 4;     // [2], 4*kHalves arrivals each (the warps working on one block)
   uint64_t* o_bar = k_bar + 6;     // [3]
   uint64_t* v_bar = k_bar + 9;
-  uint64_t* e_bar = k_bar + 10;    // [2] by tile parity, 8 arrivals: epilogue of the tile done
+  uint64_t* e_bar = k_bar + 10;    // [2] by tile parity, kWarps arrivals: epilogue of the tile done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_bar + 12);
-  const uint32_t sMul = smem_u32(tail + 128);           // [384] f32
-  const uint32_t sAdd = sMul + 384 * 4;                 // [384] f32
-  const uint32_t sStatM = sAdd + 384 * 4;               // [8 block slots][128] f32 block max
-  const uint32_t sStatL = sStatM + 8 * 128 * 4;         // [8 block slots][128] f32 block sum
+  const uint32_t sMul = smem_u32(tail + 128);               // [320] f32
+  const uint32_t sAdd = sMul + kWgTableCols * 4;            // [320] f32
+  const uint32_t sClean = sAdd + kWgTableCols * 4;          // [32] u32: 16-key chunk has no masked key
+  const uint32_t sStatM = sClean + 128;                     // [8 block slots][128] f32 block max
+  const uint32_t sStatL = sStatM + 8 * 128 * 4;             // [8 block slots][2 halves][128] f32 sums
+  const uint32_t sMax = sStatL + 16 * 128 * 4;              // [2 tile parities][2 blocks][2 halves][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool is_control = warp == kAttnComputeWarps;
+  const bool is_control = warp == kWarps;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -814,8 +852,8 @@ attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
     mbar_init(q_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_bar[i], 1);
-      mbar_init(&p_bar[i], kAttnComputeWarps / 2);
-      mbar_init(&e_bar[i], kAttnComputeWarps);
+      mbar_init(&p_bar[i], 4 * kHalves);
+      mbar_init(&e_bar[i], kWarps);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&o_bar[i], 1);
     fence_barrier_init();
@@ -917,27 +955,44 @@ attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
     __syncwarp();
   } else {
     // ===================== softmax + epilogue warps =====================
-    const int wg = warp >> 2, quarter = warp & 3;
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int blk = kHalves == 2 ? (grp >> 1) : grp;          // key block == S / P buffer
+    const int half = kHalves == 2 ? (grp & 1) : 0;            // column half inside the block
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int k0 = wg ? p.w0 : 0, W = wg ? p.w1 : p.w0;   // this warpgroup's key block
-    const uint32_t ts = tmem_base + wg * 160 + lane_off;
-    const uint32_t pbuf = smem_u32(sP) + wg * kPPBuf;
+    const int k0 = blk ? p.w0 : 0, W = blk ? p.w1 : p.w0;
+    const int nch = W / 16;                                   // 16-key chunks of the block
+    const int cb = kHalves == 2 ? (half ? (nch + 1) / 2 : 0) : 0;
+    const int ce = kHalves == 2 ? (half ? nch : (nch + 1) / 2) : nch;
+    const uint32_t ts = tmem_base + blk * 160 + lane_off;
+    const uint32_t pbuf = smem_u32(sP) + blk * kPPBuf;
     const uint32_t ma0 = sMul + k0 * 4, aa0 = sAdd + k0 * 4;
-    uint32_t gt = 0;                                       // global tile counter of this CTA
+    const uint32_t clean0 = sClean + (k0 >> 4) * 4;
+    const int ocol = grp * kOCols;
+    const float c_log2 = p.scale_log2;
+    uint32_t gt = 0;                                          // global tile counter of this CTA
     for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
       const int b = bh / p.H, h = bh - b * p.H;
-      for (int j = threadIdx.x; j < 384; j += kAttnComputeWarps * 32) {
+      // mask tables + per-chunk "no masked key" flags.  j advances by whole warps, so the ballot
+      // below always sees 32 consecutive key columns with a warp-uniform trip count.
+      for (int j = threadIdx.x; j < kWgTableCols; j += kWarps * 32) {
         float mul = 0.f, add = -INFINITY;
+        bool clean = false;
         if (j < p.n) {
           const bool keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
           mul = keep ? p.scale_log2 : 0.f;
           add = keep ? 0.f : -FLT_MAX;
+          clean = keep;
         }
         sts_f(sMul + j * 4, mul);
         sts_f(sAdd + j * 4, add);
+        const uint32_t bal = __ballot_sync(0xffffffffu, clean);
+        if (lane == 0) {
+          sts_u32(sClean + (j >> 4) * 4, (bal & 0xffffu) == 0xffffu ? 1u : 0u);
+          sts_u32(sClean + ((j >> 4) + 1) * 4, (bal >> 16) == 0xffffu ? 1u : 0u);
+        }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
 
       auto epilogue = [&](int t, uint32_t gtile) {
         const uint32_t g0 = 2 * gtile, g1 = g0 + 1;
@@ -946,27 +1001,36 @@ attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
         tcgen05_fence_after();
         const int q_idx = t * kTile + row;
         const float m0 = lds_f(sStatM + ((g0 & 7) * 128 + row) * 4);
-        const float l0 = lds_f(sStatL + ((g0 & 7) * 128 + row) * 4);
         const float m1 = lds_f(sStatM + ((g1 & 7) * 128 + row) * 4);
-        const float l1 = lds_f(sStatL + ((g1 & 7) * 128 + row) * 4);
+        float l0 = lds_f(sStatL + (((g0 & 7) * 2) * 128 + row) * 4);
+        float l1 = lds_f(sStatL + (((g1 & 7) * 2) * 128 + row) * 4);
+        if constexpr (kHalves == 2) {
+          l0 += lds_f(sStatL + (((g0 & 7) * 2 + 1) * 128 + row) * 4);
+          l1 += lds_f(sStatL + (((g1 & 7) * 2 + 1) * 128 + row) * 4);
+        }
         const float m = fmaxf(m0, m1);
         const float a0 = ex2_approx(m0 - m), a1 = ex2_approx(m1 - m);
         const float L = a0 * l0 + a1 * l1;
         const float inv = 1.f / L;
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(tmem_base + 320 + (g0 % 3) * kDh + lane_off + wg * 32, v0);
-        tmem_ld_32x32(tmem_base + 320 + (g1 % 3) * kDh + lane_off + wg * 32, v1);
+        uint32_t v0[kOCols], v1[kOCols];
+        if constexpr (kOCols == 32) {
+          tmem_ld_32x32(tmem_base + 320 + (g0 % 3) * kDh + lane_off + ocol, v0);
+          tmem_ld_32x32(tmem_base + 320 + (g1 % 3) * kDh + lane_off + ocol, v1);
+        } else {
+          tmem_ld_32x16(tmem_base + 320 + (g0 % 3) * kDh + lane_off + ocol, v0);
+          tmem_ld_32x16(tmem_base + 320 + (g1 % 3) * kDh + lane_off + ocol, v1);
+        }
         tmem_ld_wait();
         // both O buffers are in registers: release the ring slots before the global stores
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&e_bar[gtile & 1]);
         if (q_idx < p.n) {
-          if (wg == 0) p.lse[((long long)b * p.H + h) * p.n + q_idx] = m + log2f(L);
-          bf16* dst = p.o + ((long long)b * p.n + q_idx) * p.ldo + h * kDh + wg * 32;
+          if (grp == 0) p.lse[((long long)b * p.H + h) * p.n + q_idx] = m + log2f(L);
+          bf16* dst = p.o + ((long long)b * p.n + q_idx) * p.ldo + h * kDh + ocol;
           const float c0 = a0 * inv, c1 = a1 * inv;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
+          for (int i = 0; i < kOCols; i += 8) {
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -980,49 +1044,69 @@ attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
       };
 
       for (int t = 0; t < T; ++t, ++gt) {
-        const uint32_t gb = 2 * gt + wg;                   // this warpgroup's block of tile t
+        const uint32_t gb = 2 * gt + blk;                  // this warp's block of tile t
         const bool warp_alive = t * kTile + quarter * 32 < p.n;
-        mbar_wait(&s_bar[wg], gt & 1);
+        mbar_wait(&s_bar[blk], gt & 1);
         tcgen05_fence_after();
-        float m2 = -INFINITY, sum = 0.f;
+        float m_scaled = -INFINITY, m_raw = -INFINITY, sum = 0.f;
         if (warp_alive) {
-          for (int c = 0; c < W; c += 32) {
-            if (c + 32 <= W) {
+          for (int c = cb; c < ce;) {
+            if (kHalves == 1 && c + 2 <= ce) {
               uint32_t w[32];
-              tmem_ld_32x32(ts + c, w);
+              tmem_ld_32x32(ts + c * 16, w);
+              const bool fast = kFast && lds_u32(clean0 + c * 4) != 0 && lds_u32(clean0 + (c + 1) * 4) != 0;
               tmem_ld_wait();
-              m2 = wg_pass_max<32>(w, ma0 + c * 4, aa0 + c * 4, m2);
+              if (fast) wg_pass_max<32, true>(w, 0, 0, m_scaled, m_raw);
+              else wg_pass_max<32, false>(w, ma0 + c * 64, aa0 + c * 64, m_scaled, m_raw);
+              c += 2;
             } else {
               uint32_t w[16];
-              tmem_ld_32x16(ts + c, w);
+              tmem_ld_32x16(ts + c * 16, w);
+              const bool fast = kFast && lds_u32(clean0 + c * 4) != 0;
               tmem_ld_wait();
-              m2 = wg_pass_max<16>(w, ma0 + c * 4, aa0 + c * 4, m2);
+              if (fast) wg_pass_max<16, true>(w, 0, 0, m_scaled, m_raw);
+              else wg_pass_max<16, false>(w, ma0 + c * 64, aa0 + c * 64, m_scaled, m_raw);
+              c += 1;
             }
           }
         }
-        // this warpgroup's P buffer was last read by PV(gb-2)
+        // scale > 0 (checked by the launcher for the fast variants): max commutes with the scaling
+        float m2 = kFast ? fmaxf(m_scaled, m_raw * c_log2) : m_scaled;
+        if constexpr (kHalves == 2) {
+          const uint32_t slot = sMax + ((((gt & 1) * 2 + blk) * 2) * 128 + row) * 4;
+          sts_f(slot + half * 128 * 4, m2);
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + blk * 4 + quarter) : "memory");
+          m2 = fmaxf(m2, lds_f(slot + (half ^ 1) * 128 * 4));
+        }
+        // the block's P buffer was last read by PV(gb-2)
         if (gb >= 2) mbar_wait(&o_bar[(gb - 2) % 3], ((gb - 2) / 3) & 1);
         if (warp_alive) {
-          for (int c = 0; c < W; c += 32) {
-            if (c + 32 <= W) {
+          for (int c = cb; c < ce;) {
+            if (kHalves == 1 && c + 2 <= ce) {
               uint32_t w[32];
-              tmem_ld_32x32(ts + c, w);
+              tmem_ld_32x32(ts + c * 16, w);
+              const bool fast = kFast && lds_u32(clean0 + c * 4) != 0 && lds_u32(clean0 + (c + 1) * 4) != 0;
               tmem_ld_wait();
-              sum += wg_pass_exp<32>(w, ma0 + c * 4, aa0 + c * 4, m2, pbuf, row, c);
+              sum += fast ? wg_pass_exp<32, true>(w, 0, 0, m2, c_log2, pbuf, row, c * 16)
+                          : wg_pass_exp<32, false>(w, ma0 + c * 64, aa0 + c * 64, m2, c_log2, pbuf, row, c * 16);
+              c += 2;
             } else {
               uint32_t w[16];
-              tmem_ld_32x16(ts + c, w);
+              tmem_ld_32x16(ts + c * 16, w);
+              const bool fast = kFast && lds_u32(clean0 + c * 4) != 0;
               tmem_ld_wait();
-              sum += wg_pass_exp<16>(w, ma0 + c * 4, aa0 + c * 4, m2, pbuf, row, c);
+              sum += fast ? wg_pass_exp<16, true>(w, 0, 0, m2, c_log2, pbuf, row, c * 16)
+                          : wg_pass_exp<16, false>(w, ma0 + c * 64, aa0 + c * 64, m2, c_log2, pbuf, row, c * 16);
+              c += 1;
             }
           }
         }
-        sts_f(sStatM + ((gb & 7) * 128 + row) * 4, m2);
-        sts_f(sStatL + ((gb & 7) * 128 + row) * 4, sum);
+        if (half == 0) sts_f(sStatM + ((gb & 7) * 128 + row) * 4, m2);
+        sts_f(sStatL + (((gb & 7) * 2 + half) * 128 + row) * 4, sum);
         fence_proxy_async_smem();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_bar[wg]);
+        if (lane == 0) mbar_arrive(&p_bar[blk]);
         if (t > 0) epilogue(t - 1, gt - 1);                // deferred behind this tile's softmax
       }
       epilogue(T - 1, gt - 1);
@@ -1051,14 +1135,15 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
   const int nkb = (q.n + kTile - 1) / kTile;
   static const int variant = [] {
     const char* e = getenv("XCLIP_ATTN_PP_VARIANT");
-    return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;
+    return (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 0;
   }();
-  // barriers + mask tables + per-row exchange buffers (variant 4: 2 x 8-slot statistics ring)
-  const int tail_bytes = 128 + 2 * 384 * 4 + (variant == 4 ? 16 * 128 * 4 : (4 + 8) * 128 * 4);
+  XCLIP_REQUIRE(variant < 6 || q.scale_log2 > 0.f, "attn_fwd: the fast-chunk variants need scale > 0");
+  // barriers + mask tables + per-row exchange buffers
+  const int tail_bytes = variant >= 4 ? kWgTailBytes : 128 + 2 * 384 * 4 + (4 + 8) * 128 * 4;
   const int smem = (1 + 2 * nkb) * kBoxBytes + 2 * kPPBuf + tail_bytes;
   static bool configured = false;
   if (!configured) {
-    const int max_smem = (1 + 6) * kBoxBytes + 2 * kPPBuf + 128 + 2 * 384 * 4 + 16 * 128 * 4;
+    const int max_smem = (1 + 6) * kBoxBytes + 2 * kPPBuf + kWgTailBytes;
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<0>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<1>,
@@ -1067,8 +1152,14 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<3>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel<1, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel<2, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel<1, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel<2, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   long long grid = num_sms();
@@ -1077,7 +1168,10 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
     case 1: attn_fwd_pp_kernel<1><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
     case 2: attn_fwd_pp_kernel<2><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
     case 3: attn_fwd_pp_kernel<3><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
-    case 4: attn_fwd_wg_kernel<<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
+    case 4: attn_fwd_wg_kernel<1, false><<<(int)grid, 9 * 32, smem, stream>>>(tm, p); break;
+    case 5: attn_fwd_wg_kernel<2, false><<<(int)grid, 17 * 32, smem, stream>>>(tm, p); break;
+    case 6: attn_fwd_wg_kernel<1, true><<<(int)grid, 9 * 32, smem, stream>>>(tm, p); break;
+    case 7: attn_fwd_wg_kernel<2, true><<<(int)grid, 17 * 32, smem, stream>>>(tm, p); break;
     default: attn_fwd_pp_kernel<0><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
   }
   XCLIP_LAUNCH_CHECK("attn_fwd_pp_kernel");
