@@ -11,3 +11,9 @@ XCLIP_ATTN_TAIL=1 timeout 45 python tools/pp_check.py 2>&1 | grep -E "FAIL|time|
 echo "== bench (default), then with the tail path"
 timeout 90 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
 XCLIP_ATTN_TAIL=1 timeout 90 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
+if [ -f x_clip_b200/libxclip_b200_elect.so ]; then
+  echo "== elect.sync build (XCLIP_BUILD_ELECT=1 python -m x_clip_b200.build, made before gpurun)"
+  XCLIP_LIB_VARIANT=elect timeout 240 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+  XCLIP_LIB_VARIANT=elect timeout 60 python tools/pp_check.py 2>&1 | grep -E "FAIL|time|ALL|SOME|rror"
+  XCLIP_LIB_VARIANT=elect timeout 90 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
+fi

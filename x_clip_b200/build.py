@@ -14,8 +14,11 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "csrc" / "build"
-LIB = PKG / "libxclip_b200.so"
+# XCLIP_BUILD_ELECT=1 builds the experimental elect.sync variant NEXT TO the default library
+# (own object directory, libxclip_b200_elect.so); `XCLIP_LIB_VARIANT=elect` makes _lib.py load it.
+_VARIANT = "elect" if os.environ.get("XCLIP_BUILD_ELECT") == "1" else ""
+OBJ = PKG / "csrc" / ("build_" + _VARIANT if _VARIANT else "build")
+LIB = PKG / ("libxclip_b200_" + _VARIANT + ".so" if _VARIANT else "libxclip_b200.so")
 
 NVCC_FLAGS = [
     "-O3",
@@ -25,6 +28,14 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
 ]
+
+
+def _extra_flags() -> list:
+    """Opt-in code-generation switches (see csrc/common.cuh); empty for the default build."""
+    flags = []
+    if os.environ.get("XCLIP_BUILD_ELECT") == "1":
+        flags.append("-DXCLIP_USE_ELECT=1")
+    return flags
 
 
 def _nvcc() -> str:
@@ -44,7 +55,7 @@ def _compile(src: Path, verbose: bool) -> Path:
     dep_m = max(src.stat().st_mtime, _newest_header_mtime())
     if obj.exists() and obj.stat().st_mtime > dep_m:
         return obj
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *_extra_flags(), "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

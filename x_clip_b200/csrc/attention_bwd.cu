@@ -173,7 +173,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   if (is_control) {
     // ===================== control warp =====================
-    if (lane == 0) {
+    if (XCLIP_ONE_LANE(lane)) {
       // Coordinates of a pair are tracked incrementally (no divisions on this single-thread
       // critical path): `cur` is the pair whose gradient MMAs are issued, `nxt` the one whose
       // tiles are prefetched / whose S,dP are issued, `kvn` the next key step to prefetch.

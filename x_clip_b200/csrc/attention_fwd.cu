@@ -183,7 +183,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
         sts_f(sAdd + j * 4, add);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-    } else if (lane == 0) {
+    } else if (XCLIP_ONE_LANE(lane)) {
       mbar_arrive_expect_tx(kv_bar, 2 * nkb * kBoxBytes);
       for (int i = 0; i < nkb; ++i) {
         tma_load_3d(sK + i * kBoxBytes, &tm_qkv, kv_bar, inner + h * kDh, i * kTile, b);
@@ -193,7 +193,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdParams 
 
     if (is_control) {
       // ===================== control warp: TMA + MMA issue, software pipelined ============
-      if (lane == 0) {
+      if (XCLIP_ONE_LANE(lane)) {
         // operand descriptors are built once; the loops only add compile-time offsets
         // (descriptor address units are 16 bytes)
         const uint64_t desc_q0 = make_smem_desc(smem_u32(sQ), 0, 1024);
@@ -460,7 +460,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
   const int inner = p.H * kDh;
 
   if (is_control) {
-    if (lane == 0) {
+    if (XCLIP_ONE_LANE(lane)) {
       const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 0, 1024);
       const uint64_t desc_k = make_smem_desc(smem_u32(sK), 0, 1024);
       const uint64_t desc_v = make_smem_desc(smem_u32(sV), 8192, 1024);
@@ -870,7 +870,7 @@ attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
   const int inner = p.H * kDh;
 
   if (is_control) {
-    if (lane == 0) {
+    if (XCLIP_ONE_LANE(lane)) {
       const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 0, 1024);
       const uint64_t desc_k = make_smem_desc(smem_u32(sK), 0, 1024);
       const uint64_t desc_v = make_smem_desc(smem_u32(sV), 8192, 1024);

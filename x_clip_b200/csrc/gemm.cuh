@@ -125,7 +125,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 4 && XCLIP_ONE_LANE(lane)) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.use_tma_store) tma_prefetch_desc(&tmC);
@@ -138,7 +138,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (XCLIP_ONE_LANE(lane)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -196,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (XCLIP_ONE_LANE(lane)) {
           const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
           const uint64_t adesc =
