@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from test_gpu_attention import _ref_attention, _mk
 
 dev = torch.device("cuda:0")
-tag = ("tail" if os.environ.get("XCLIP_ATTN_TAIL") == "1" else "notail") + "/v" + os.environ.get("XCLIP_ATTN_PP_VARIANT", "0")
+tag = ("tail" if os.environ.get("XCLIP_ATTN_TAIL") == "1" else "notail") + "/v" + os.environ.get("XCLIP_ATTN_PP_VARIANT", "0") + ("/bwd16" if os.environ.get("XCLIP_ATTN_BWD16") == "1" else "")
 ok = True
 for (B, n, H, masked) in [(2, 129, 2, True), (40, 129, 4, False), (2, 145, 3, False), (2, 197, 12, False), (2, 257, 8, True),
                           (1, 320, 2, True), (40, 257, 8, True), (30, 197, 12, False), (50, 300, 4, True),
