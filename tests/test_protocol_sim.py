@@ -28,3 +28,14 @@ def test_redundant_waits_are_implied_by_the_in_order_tensor_pipe(mutate):
     # these two waits in the kernels are belt and braces; the model agrees.
     assert P.run("pp", trials=30, mutate=mutate)
     assert P.run("wg2", trials=30, mutate=mutate)
+
+
+@pytest.mark.parametrize("mode", ["bwd", "bwd_split"])
+def test_backward_protocols_are_hazard_free(mode):
+    assert P.run_bwd(mode, trials=30)
+
+
+@pytest.mark.parametrize("mutate", ["no_hfree", "no_g_wait"])
+def test_model_detects_broken_backward_split(mutate):
+    with pytest.raises(P.Hazard):
+        P.run_bwd("bwd_split", trials=60, mutate=mutate)

@@ -10,7 +10,7 @@ randomised latencies.  Every buffer carries a version tag; the model raises on
   * a write into a buffer that still has readers, or a read of a buffer being written,
   * a deadlock (nothing runnable before all programs finished),
   * an mbarrier wait that could alias (waiter two phases behind).
-Usage: python tools/protocol_sim.py [pp|wg1|wg2] [trials]     (tests/test_protocol_sim.py runs it)
+Usage: python tools/protocol_sim.py [pp|wg1|wg2|bwd|bwd_split] [trials]     (tests/test_protocol_sim.py runs it)
 """
 from __future__ import annotations
 
@@ -381,6 +381,146 @@ def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
                     sim.spawn(warp_wg(q, blk, h))
 
 
+# ------------------------------------------------------------------------------------------
+# attention backward (csrc/attention_bwd.cu).  mode 'bwd': the shipped kernel; 'bwd_split': the
+# planned variant whose S/dP tile is produced in two 64-key halves with their own barriers so the
+# next pair's first half is computed by the tensor pipe while the softmax warps still work on the
+# second half of the current pair.
+def build_bwd(sim: Sim, mode: str, items: int, ntiles: int, mutate: str = ""):
+    split = mode == "bwd_split"
+    nwarps = 8
+    B = lambda name, c: MBar(sim, name, c)
+    kv_bar = [B(f"kv_bar{i}", 1) for i in range(2)]
+    qdo_bar = [B(f"qdo_bar{i}", 1) for i in range(2)]
+    s_bar = [B(f"s_bar{i}", 1) for i in range(2)]        # 'bwd' uses s_bar[0] only
+    hfree = B("hfree0", nwarps)
+    pds_bar, g_bar, dq_bar = B("pds_bar", nwarps), B("g_bar", 1), B("dq_bar", 1)
+    all_bar = HwBarrier(sim, nwarps)
+    pairs = [(bh, j, i) for bh in range(items) for j in range(ntiles) for i in range(ntiles)]
+    ksteps = [(bh, j) for bh in range(items) for j in range(ntiles)]
+    npairs = len(pairs)
+    kc_of = {pc: pc // ntiles for pc in range(npairs)}
+    parts = [f"PdS.h{h}.w{w}" for h in range(2) for w in range(nwarps)]
+
+    def control():
+        def load_kv(kc):
+            sim.tma([f"KV{kc & 1}"], ksteps[kc], kv_bar[kc & 1])
+
+        def load_qdo(pc):
+            bh, j, i = pairs[pc]
+            sim.tma([f"QdO{pc & 1}"], (bh, i, pc), qdo_bar[pc & 1])
+
+        def issue_scores(pc, halves):
+            bh, j, i = pairs[pc]
+            kc = kc_of[pc]
+            reads = [(f"QdO{pc & 1}", (bh, i, pc)), (f"KV{kc & 1}", ksteps[kc])]
+            for h in halves:
+                sim.tensor_issue(("mma", reads, [(f"S{h}", pc)], 256 if split else 512))
+                sim.tensor_issue(("commit", s_bar[h]))
+
+        load_kv(0)
+        load_qdo(0)
+        yield wait(kv_bar[0], 0, 1)
+        yield wait(qdo_bar[0], 0, 1)
+        issue_scores(0, (0, 1) if split else (0,))
+        for pc in range(npairs):
+            bh, j, i = pairs[pc]
+            kc = kc_of[pc]
+            has_next = pc + 1 < npairs
+            if pc >= 1:
+                yield wait(g_bar, (pc - 1) & 1, pc)
+            if i == 0 and kc + 1 < len(ksteps):
+                load_kv(kc + 1)
+            if has_next:
+                load_qdo(pc + 1)
+
+            def next_ready():
+                nkc = kc_of[pc + 1]
+                if pairs[pc + 1][2] == 0:
+                    yield wait(kv_bar[nkc & 1], (nkc >> 1) & 1, (nkc >> 1) + 1)
+                yield wait(qdo_bar[(pc + 1) & 1], ((pc + 1) >> 1) & 1, ((pc + 1) >> 1) + 1)
+
+            if split and has_next:
+                if mutate != "no_hfree":
+                    yield wait(hfree, pc & 1, pc + 1)
+                yield from next_ready()
+                yield ("delay", sim.jitter(20, 300))
+                issue_scores(pc + 1, (0,))
+            yield wait(pds_bar, pc & 1, pc + 1)
+            yield ("delay", sim.jitter(20, 300))
+            kvn, qn = f"KV{kc & 1}", f"QdO{pc & 1}"
+            kvv, qv = ksteps[kc], (bh, i, pc)
+            pds_reads = [(n, pc) for n in parts]
+            sim.tensor_issue(("mma", pds_reads + [(kvn, kvv)], [("dQ", pc)], 256))
+            sim.tensor_issue(("commit", dq_bar))
+            if split and has_next:
+                issue_scores(pc + 1, (1,))
+            sim.tensor_issue(("mma", pds_reads + [(qn, qv)], [("dKV", pc)], 512))
+            sim.tensor_issue(("commit", g_bar))
+            if (not split) and has_next:
+                yield from next_ready()
+                issue_scores(pc + 1, (0,))
+        yield wait(g_bar, (npairs - 1) & 1, npairs)
+
+    def warp(w):
+        pc = 0
+        for bh in range(items):
+            for j in range(ntiles):
+                if w < 4:
+                    sim.write(f"tables.w{w}", (bh, j))
+                yield ("hw", all_bar)
+                for i in range(ntiles):
+                    for h in ((0, 1) if split else (0,)):
+                        yield wait(s_bar[h], pc & 1, pc + 1)
+                        sim.read_begin(f"S{h}", pc)
+                        if not split and pc >= 1:
+                            yield wait(g_bar, (pc - 1) & 1, pc)
+                        sim.read_begin(f"tables.w{w & 3}", (bh, j))
+                        yield ("delay", sim.jitter(150, 1500))
+                        sim.read_end(f"tables.w{w & 3}")
+                        sim.read_end(f"S{h}")
+                        if split and h == 0:
+                            hfree.arrive()
+                            if pc >= 1 and mutate != "no_g_wait":
+                                yield wait(g_bar, (pc - 1) & 1, pc)
+                        names = [f"PdS.h{h}.w{w}"] if split else [f"PdS.h0.w{w}", f"PdS.h1.w{w}"]
+                        for nme in names:
+                            sim.write_begin(nme, pc)
+                        yield ("delay", sim.jitter(20, 300))
+                        for nme in names:
+                            sim.write_end(nme, pc)
+                    pds_bar.arrive()
+                    if j > 0:
+                        sim.read_begin(f"ws.{bh}.{i}.w{w}", j - 1)
+                        sim.read_end(f"ws.{bh}.{i}.w{w}")
+                    yield wait(dq_bar, pc & 1, pc + 1)
+                    sim.read_begin("dQ", pc)
+                    yield ("delay", sim.jitter(50, 600))
+                    sim.read_end("dQ")
+                    sim.write(f"ws.{bh}.{i}.w{w}", j)
+                    pc += 1
+                yield wait(g_bar, (pc - 1) & 1, pc)
+                sim.read_begin("dKV", pc - 1)
+                yield ("delay", sim.jitter(50, 600))
+                sim.read_end("dKV")
+
+    sim.spawn(control())
+    for w in range(nwarps):
+        sim.spawn(warp(w))
+
+
+def run_bwd(mode: str, trials: int = 100, seed0: int = 0, mutate: str = ""):
+    for trial in range(trials):
+        for ntiles in (1, 2, 3):
+            sim = Sim(seed0 + 1000 * trial + ntiles)
+            build_bwd(sim, mode, items=sim.rng.choice([1, 2, 3]), ntiles=ntiles, mutate=mutate)
+            try:
+                sim.run()
+            except Hazard as e:
+                raise Hazard(f"[{mode} ntiles={ntiles} trial={trial}] {e}") from None
+    return True
+
+
 def run(mode: str, trials: int = 200, seed0: int = 0, mutate: str = ""):
     for trial in range(trials):
         for T in (1, 2, 3):
@@ -396,5 +536,5 @@ def run(mode: str, trials: int = 200, seed0: int = 0, mutate: str = ""):
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "pp"
     trials = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-    run(mode, trials)
-    print(f"{mode}: {trials} randomised trials x T in (1,2,3): no hazard, no deadlock")
+    (run_bwd if mode.startswith("bwd") else run)(mode, trials)
+    print(f"{mode}: {trials} randomised trials x 1..3 tiles: no hazard, no deadlock")
