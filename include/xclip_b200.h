@@ -107,7 +107,9 @@ int xclip_cast_f32_bf16(const float* src, void* dst, int64_t n, xclip_stream_t s
 int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o, int64_t ldo,
                    float* lse, int B, int n, int heads, float scale, xclip_stream_t stream);
 /* delta f32 [B, heads, n] is scratch (rowsum(dO*O), written here).  dq_workspace f32
- * [B*n, heads*64] is required when n > 128 (partial dQ across key tiles), else may be NULL. */
+ * [B*n, heads*64] is required when n > 128 (partial dQ across key tiles), else may be NULL;
+ * its contents are scratch too (with XCLIP_ATTN_TAIL=1 and n = 128k+1 the first three floats of a
+ * token's 64-float slot also carry the tail-token scalars between the two backward kernels). */
 int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, const void* o,
                    int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta,
                    void* dqkv, int64_t ld_dqkv, float* dq_workspace, int B, int n, int heads,
