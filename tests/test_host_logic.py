@@ -73,3 +73,39 @@ def test_patch_dropout_matches_reference_recipe():
     assert torch.equal(out, x[torch.arange(3)[:, None], idx])
     pd.eval()
     assert pd(x) is x
+
+
+def test_constructor_and_forward_signatures_match_the_reference():
+    """Drop-in surface: same keyword names and defaults as x_clip.CLIP.__init__ /
+    forward (x_clip/x_clip.py:413-456, 597-609).  Needs the reference checkout (build container
+    only); skipped where /root/reference is absent (GPU box)."""
+    import importlib
+    import inspect
+    import os
+    import sys
+    if not os.path.isdir("/root/reference/x_clip"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref = importlib.import_module("x_clip")
+    finally:
+        sys.path.remove("/root/reference")
+    import x_clip_b200
+
+    def params(fn):
+        return {k: v.default for k, v in inspect.signature(fn).parameters.items()
+                if k not in ("self", "kwargs")}
+
+    ref_init, our_init = params(ref.CLIP.__init__), params(x_clip_b200.CLIP.__init__)
+    missing = [k for k in ref_init if k not in our_init]
+    assert not missing, f"constructor keywords of the reference missing here: {missing}"
+    for k, v in ref_init.items():
+        assert our_init[k] == v or (v is inspect.Parameter.empty) == (our_init[k] is inspect.Parameter.empty), \
+            f"default of {k}: reference {v!r}, here {our_init[k]!r}"
+        if v is not inspect.Parameter.empty:
+            assert our_init[k] == v, f"default of {k}: reference {v!r}, here {our_init[k]!r}"
+    extra = sorted(set(our_init) - set(ref_init))
+    assert extra == ["microbatch"], f"unexpected extra constructor keywords: {extra}"
+    ref_fwd, our_fwd = params(ref.CLIP.forward), params(x_clip_b200.CLIP.forward)
+    assert list(ref_fwd) == list(our_fwd), (list(ref_fwd), list(our_fwd))
+    assert ref_fwd == our_fwd
