@@ -10,7 +10,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
 import protocol_sim as P  # noqa: E402
 
 
-@pytest.mark.parametrize("mode", ["pp", "wg1", "wg2"])
+@pytest.mark.parametrize("mode", ["pp", "pp16", "wg1", "wg2"])
 def test_protocol_is_hazard_free(mode):
     assert P.run(mode, trials=40)
 

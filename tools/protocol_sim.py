@@ -10,7 +10,7 @@ randomised latencies.  Every buffer carries a version tag; the model raises on
   * a write into a buffer that still has readers, or a read of a buffer being written,
   * a deadlock (nothing runnable before all programs finished),
   * an mbarrier wait that could alias (waiter two phases behind).
-Usage: python tools/protocol_sim.py [pp|wg1|wg2|bwd|bwd_split] [trials]     (tests/test_protocol_sim.py runs it)
+Usage: python tools/protocol_sim.py [pp|pp16|wg1|wg2|bwd|bwd_split] [trials]     (tests/test_protocol_sim.py runs it)
 """
 from __future__ import annotations
 
@@ -203,7 +203,8 @@ def wait(bar, parity, want):
 
 
 # ------------------------------------------------------------------------------------------
-# protocol transcription.  mode: 'pp' (attn_fwd_pp_kernel, 8 warps, CTA-wide row barrier),
+# protocol transcription.  mode: 'pp' (attn_fwd_pp_kernel, 8 warps, CTA-wide row barrier), 'pp16'
+# (attn_fwd_pp16_kernel, 16 warps, 128-thread barrier per lane quarter),
 # 'wg1' (attn_fwd_wg_kernel<1>), 'wg2' (attn_fwd_wg_kernel<2>)
 def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
     """`mutate` breaks the protocol on purpose (the model must then raise): 'no_e_bar' (PV does not
@@ -213,13 +214,14 @@ def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
     for the softmax warps of block g-2 - also implied, by the wait inside issue_pv(g-2)), 'no_q_wait'
     (Q / K reloaded without waiting for the S MMA that reads them)."""
     halves = 2 if mode in ("pp", "wg2") else 1
-    nwarps = 16 if mode == "wg2" else 8
-    wg = mode != "pp"
+    nwarps = 16 if mode in ("wg2", "pp16") else 8
+    wg = mode not in ("pp", "pp16")
+    ngrp = 4 if mode == "pp16" else 2             # column groups per row in the pp kernels
     ring = 3 if mutate == "ring4" else 7          # statistics ring mask of the warpgroup variants
     B = lambda name, c: MBar(sim, name, c)
     k_bar, v_bar, q_bar = B("k_bar", 1), B("v_bar", 1), B("q_bar", 1)
     s_bar = [B(f"s_bar{i}", 1) for i in range(2)]
-    p_bar = [B(f"p_bar{i}", (4 * halves) if wg else 8) for i in range(2)]
+    p_bar = [B(f"p_bar{i}", (4 * halves) if wg else nwarps) for i in range(2)]
     o_bar = [B(f"o_bar{i}", 1) for i in range(3)]
     e_bar = [B(f"e_bar{i}", nwarps) for i in range(2)]
     all_bar = HwBarrier(sim, nwarps)
@@ -228,7 +230,7 @@ def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
     def p_parts(buf):          # the smem parts of P buffer `buf` (one per writing warp)
         if wg:
             return [f"P{buf}.q{q}.h{h}" for q in range(4) for h in range(halves)]
-        return [f"P{buf}.q{q}.h{h}" for q in range(4) for h in range(2)]
+        return [f"P{buf}.q{q}.h{h}" for q in range(4) for h in range(ngrp)]
 
     def control():
         g = tt = 0
@@ -294,9 +296,15 @@ def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
                     sim.read_begin(f"S{g & 1}", g)
                     yield ("delay", sim.jitter(200, 1500))
                     sim.write(f"max{g & 1}.q{q}.h{h}", g)
-                    yield ("hw", all_bar)
-                    sim.read_begin(f"max{g & 1}.q{q}.h{h ^ 1}", g)
-                    sim.read_end(f"max{g & 1}.q{q}.h{h ^ 1}")
+                    if mode == "pp16":                      # 128-thread named barrier per lane quarter
+                        if ("quad", q) not in pair_bar:
+                            pair_bar[("quad", q)] = HwBarrier(sim, 4)
+                        yield ("hw", pair_bar[("quad", q)])
+                    else:
+                        yield ("hw", all_bar)
+                    for o in range(1, ngrp):
+                        sim.read_begin(f"max{g & 1}.q{q}.h{(h + o) % ngrp}", g)
+                        sim.read_end(f"max{g & 1}.q{q}.h{(h + o) % ngrp}")
                     if g >= 2 and mutate != "no_p_free":
                         yield wait(o_bar[(g - 2) % 3], ((g - 2) // 3) & 1, (g - 2) // 3 + 1)
                     sim.write_begin(f"P{g & 1}.q{q}.h{h}", g)
@@ -315,8 +323,9 @@ def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
         yield wait(o_bar[g0 % 3], (g0 // 3) & 1, g0 // 3 + 1)
         yield wait(o_bar[g1 % 3], (g1 // 3) & 1, g1 // 3 + 1)
         for gg in (g0, g1):
-            sim.read_begin(stat(gg & 3, q, h ^ 1), gg)
-            sim.read_end(stat(gg & 3, q, h ^ 1))
+            for o in range(1, ngrp):
+                sim.read_begin(stat(gg & 3, q, (h + o) % ngrp), gg)
+                sim.read_end(stat(gg & 3, q, (h + o) % ngrp))
             sim.read_begin(f"O{gg % 3}", gg)
         yield ("delay", sim.jitter(50, 800))
         for gg in (g0, g1):
@@ -370,9 +379,9 @@ def build(sim: Sim, mode: str, items: int, T: int, mutate: str = ""):
         yield ("delay", sim.jitter(50, 800))          # global stores
 
     sim.spawn(control())
-    if mode == "pp":
+    if mode in ("pp", "pp16"):
         for q in range(4):
-            for h in range(2):
+            for h in range(ngrp):
                 sim.spawn(warp_pp(q, h))
     else:
         for q in range(4):

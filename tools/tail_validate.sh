@@ -17,7 +17,7 @@ tail)
   XCLIP_ATTN_TAIL=1 timeout 45 python tools/pp_check.py 2>&1 | summ 8
   ;;
 variants)
-  for v in 0 1 2 3 4 5 6 7; do
+  for v in 0 1 2 3 4 5 6 7 8 9; do
     echo "== [variants] forward ping-pong variant $v"
     XCLIP_ATTN_PP_VARIANT=$v timeout 45 python tools/pp_check.py 2>&1 | summ 8
   done

@@ -1121,6 +1121,284 @@ attn_fwd_wg_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParam
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-warp ping-pong variant (XCLIP_ATTN_PP_VARIANT=8 / 9 with the fast unmasked chunks;
+// experimental - DESIGN.md section 9).  The validated ping-pong protocol and issue thread of
+// attn_fwd_pp_kernel (S look-ahead of one block, O ring of three) with 16 softmax warps: four
+// warps share a query row (a quarter of the block's key chunks each), so four warps per
+// scheduler hide the TMEM / MUFU / shared-memory latencies that dominate the 8-warp kernel
+// (13 % issue utilisation, profiles/r1_ncu_attn_pp_stalls.md).  The row max is exchanged between
+// the four warps of a lane quarter through a 128-thread named barrier.
+constexpr int kPP16Warps = 16;
+constexpr int kPP16Threads = (kPP16Warps + 1) * 32;
+constexpr int kPP16TailBytes = 128 + 2 * kWgTableCols * 4 + 128 + 2 * 4 * 128 * 4 + 4 * 4 * 128 * 4;
+
+template <bool kFast>
+__global__ void __launch_bounds__(kPP16Threads, 1)
+attn_fwd_pp16_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPPParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nkb = (p.n + kTile - 1) / kTile;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kBoxBytes;
+  uint8_t* sV = sK + nkb * kBoxBytes;
+  uint8_t* sP = sV + nkb * kBoxBytes;           // 2 buffers
+  uint8_t* tail = sP + 2 * kPPBuf;
+  uint64_t* k_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* q_bar = k_bar + 1;
+  uint64_t* s_bar = k_bar + 2;     // [2]
+  uint64_t* p_bar = k_bar + 4;     // [2], 16 arrivals
+  uint64_t* o_bar = k_bar + 6;     // [3]
+  uint64_t* v_bar = k_bar + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_bar + 10);
+  const uint32_t sMul = smem_u32(tail + 128);               // [320] f32
+  const uint32_t sAdd = sMul + kWgTableCols * 4;            // [320] f32
+  const uint32_t sClean = sAdd + kWgTableCols * 4;          // [32] u32
+  const uint32_t sMax = sClean + 128;                       // [2 block parities][4 groups][128] f32
+  const uint32_t sSum = sMax + 2 * 4 * 128 * 4;             // [4 block slots][4 groups][128] f32
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool is_control = warp == kPP16Warps;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    mbar_init(k_bar, 1);
+    mbar_init(v_bar, 1);
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_bar[i], 1); mbar_init(&p_bar[i], kPP16Warps); }
+    for (int i = 0; i < 3; ++i) mbar_init(&o_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (is_control) {
+    if (lane == 0) tma_prefetch_desc(&tm_qkv);
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = p.q_tiles;
+  const int inner = p.H * kDh;
+
+  if (is_control) {
+    if (XCLIP_ONE_LANE(lane)) {
+      const uint64_t desc_q = make_smem_desc(smem_u32(sQ), 0, 1024);
+      const uint64_t desc_k = make_smem_desc(smem_u32(sK), 0, 1024);
+      const uint64_t desc_v = make_smem_desc(smem_u32(sV), 8192, 1024);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, kMajorK, kMajorMN);
+      const uint32_t idesc_s0 = make_idesc_bf16(kTile, p.w0, kMajorK, kMajorK);
+      const uint32_t idesc_s1 = make_idesc_bf16(kTile, p.w1, kMajorK, kMajorK);
+      auto issue_pv = [&](uint32_t gb) {        // O[gb % 3] = P(gb) V_blk(gb)
+        const int kb = gb & 1;
+        const int k0 = kb ? p.w0 : 0, W = kb ? p.w1 : p.w0;
+        mbar_wait(&p_bar[gb & 1], (gb >> 1) & 1);
+        tcgen05_fence_after();
+        const uint64_t pd = make_smem_desc(smem_u32(sP) + (gb & 1) * kPPBuf, 0, 1024);
+        const uint64_t vd = desc_v + ((k0 * 128) >> 4);
+        const uint32_t td = tmem_base + 320 + (gb % 3) * kDh;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (k < W / 16)
+            umma_bf16(td, pd + ((k >> 2) * (kBoxBytes >> 4) + (k & 3) * 2), vd + k * 128, idesc_pv,
+                      k > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_bar[gb % 3]);
+      };
+      // K + Q(tile 0) and V of the NEXT (b,h) are fetched as soon as their smem is dead: K/Q after
+      // the last S of this item retired, V after its last PV.
+      auto load_kq = [&](int bh2) {
+        const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+        mbar_arrive_expect_tx(k_bar, nkb * kBoxBytes);
+        for (int i = 0; i < nkb; ++i)
+          tma_load_3d(sK + i * kBoxBytes, &tm_qkv, k_bar, inner + h2 * kDh, i * kTile, b2);
+        mbar_arrive_expect_tx(q_bar, kBoxBytes);
+        tma_load_3d(sQ, &tm_qkv, q_bar, h2 * kDh, 0, b2);
+      };
+      auto load_v = [&](int bh2) {
+        const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+        mbar_arrive_expect_tx(v_bar, nkb * kBoxBytes);
+        for (int i = 0; i < nkb; ++i)
+          tma_load_3d(sV + i * kBoxBytes, &tm_qkv, v_bar, 2 * inner + h2 * kDh, i * kTile, b2);
+      };
+      uint32_t g = 0, tt = 0, kvc = 0;          // global block / tile / (b,h) counters of this CTA
+      const int total = p.B * p.H;
+      if ((int)blockIdx.x < total) { load_kq(blockIdx.x); load_v(blockIdx.x); }
+      for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++kvc) {
+        const int b = bh / p.H, h = bh - b * p.H;
+        const int bh_next = bh + gridDim.x;
+        mbar_wait(k_bar, kvc & 1);
+        for (int t = 0; t < T; ++t) {
+          for (int kb = 0; kb < 2; ++kb, ++g) {
+            const int k0 = kb ? p.w0 : 0;
+            if (kb == 0) { mbar_wait(q_bar, tt & 1); ++tt; }
+            if (g >= 2) mbar_wait(&p_bar[g & 1], ((g - 2) >> 1) & 1);   // S[g&1] consumed
+            tcgen05_fence_after();
+            {
+              const uint64_t kd = desc_k + ((k0 * 128) >> 4);
+              const uint32_t ts = tmem_base + (g & 1) * 160;
+              const uint32_t idesc = kb ? idesc_s1 : idesc_s0;
+#pragma unroll
+              for (int k = 0; k < kDh / 16; ++k)
+                umma_bf16(ts, desc_q + 2 * k, kd + 2 * k, idesc, k > 0 ? 1u : 0u);
+              umma_commit(&s_bar[g & 1]);
+            }
+            if (kb == 1) {
+              if (t + 1 < T) {                  // Q(t) is dead once S(g) retired: fetch Q(t+1)
+                mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+                mbar_arrive_expect_tx(q_bar, kBoxBytes);
+                tma_load_3d(sQ, &tm_qkv, q_bar, h * kDh, (t + 1) * kTile, b);
+              } else if (bh_next < total) {     // K and Q of this item are dead
+                mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+                load_kq(bh_next);
+              }
+            }
+            if (t == 0 && kb == 1) mbar_wait(v_bar, kvc & 1);
+            if (!(t == 0 && kb == 0)) issue_pv(g - 1);   // PV lags S by one block
+          }
+        }
+        issue_pv(g - 1);
+        // V / P smem are reused by the next (b,h): wait until the last PV retired
+        mbar_wait(&o_bar[(g - 1) % 3], ((g - 1) / 3) & 1);
+        if (bh_next < total) load_v(bh_next);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue warps =====================
+    const int grp = warp >> 2, quarter = warp & 3;            // grp: column group 0..3 of the row
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int ocol = grp * 16;
+    const float c_log2 = p.scale_log2;
+    uint32_t g = 0;
+    for (int bh = blockIdx.x; bh < p.B * p.H; bh += gridDim.x) {
+      const int b = bh / p.H, h = bh - b * p.H;
+      for (int j = threadIdx.x; j < kWgTableCols; j += kPP16Warps * 32) {
+        float mul = 0.f, add = -INFINITY;
+        bool clean = false;
+        if (j < p.n) {
+          const bool keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
+          mul = keep ? p.scale_log2 : 0.f;
+          add = keep ? 0.f : -FLT_MAX;
+          clean = keep;
+        }
+        sts_f(sMul + j * 4, mul);
+        sts_f(sAdd + j * 4, add);
+        const uint32_t bal = __ballot_sync(0xffffffffu, clean);   // whole warps, 32 consecutive keys
+        if (lane == 0) {
+          sts_u32(sClean + (j >> 4) * 4, (bal & 0xffffu) == 0xffffu ? 1u : 0u);
+          sts_u32(sClean + ((j >> 4) + 1) * 4, (bal >> 16) == 0xffffu ? 1u : 0u);
+        }
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+
+      float m_blk[2] = {0.f, 0.f}, l_own[2] = {0.f, 0.f};
+      float pm0 = 0.f, pm1 = 0.f, pl0 = 0.f, pl1 = 0.f;   // previous tile's block statistics
+
+      auto epilogue = [&](int t, uint32_t g0, float m0, float m1, float l0o, float l1o) {
+        const uint32_t g1 = g0 + 1;
+        mbar_wait(&o_bar[g0 % 3], (g0 / 3) & 1);
+        mbar_wait(&o_bar[g1 % 3], (g1 / 3) & 1);
+        tcgen05_fence_after();
+        const int q_idx = t * kTile + row;
+        float l0 = l0o, l1 = l1o;
+#pragma unroll
+        for (int o = 1; o < 4; ++o) {                      // the other three column groups' sums
+          l0 += lds_f(sSum + (((g0 & 3) * 4 + ((grp + o) & 3)) * 128 + row) * 4);
+          l1 += lds_f(sSum + (((g1 & 3) * 4 + ((grp + o) & 3)) * 128 + row) * 4);
+        }
+        const float m = fmaxf(m0, m1);
+        const float a0 = ex2_approx(m0 - m), a1 = ex2_approx(m1 - m);
+        const float L = a0 * l0 + a1 * l1;
+        const float inv = 1.f / L;
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x16(tmem_base + 320 + (g0 % 3) * kDh + lane_off + ocol, v0);
+        tmem_ld_32x16(tmem_base + 320 + (g1 % 3) * kDh + lane_off + ocol, v1);
+        tmem_ld_wait();
+        if (q_idx < p.n) {
+          if (grp == 0) p.lse[((long long)b * p.H + h) * p.n + q_idx] = m + log2f(L);
+          bf16* dst = p.o + ((long long)b * p.n + q_idx) * p.ldo + h * kDh + ocol;
+          const float c0 = a0 * inv, c1 = a1 * inv;
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              f[e] = __uint_as_float(v0[i + e]) * c0 + __uint_as_float(v1[i + e]) * c1;
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(dst + i) = o;
+          }
+        }
+        tcgen05_fence_before();
+      };
+
+      for (int t = 0; t < T; ++t) {
+        const bool warp_alive = t * kTile + quarter * 32 < p.n;
+        for (int kb = 0; kb < 2; ++kb, ++g) {
+          const int k0 = kb ? p.w0 : 0, W = kb ? p.w1 : p.w0;
+          const int nch = W / 16;                           // 16-key chunks, split over 4 groups
+          const int base = nch >> 2, rem = nch & 3;
+          const int cb = warp_alive ? grp * base + min(grp, rem) : 0;
+          const int ce = warp_alive ? cb + base + (grp < rem ? 1 : 0) : 0;
+          const uint32_t ts = tmem_base + (g & 1) * 160 + lane_off;
+          const uint32_t ma0 = sMul + k0 * 4, aa0 = sAdd + k0 * 4;
+          const uint32_t clean0 = sClean + (k0 >> 4) * 4;
+          mbar_wait(&s_bar[g & 1], (g >> 1) & 1);
+          tcgen05_fence_after();
+          float m_scaled = -INFINITY, m_raw = -INFINITY, sum = 0.f;
+          for (int c = cb; c < ce; ++c) {
+            uint32_t w[16];
+            tmem_ld_32x16(ts + c * 16, w);
+            const bool fast = kFast && lds_u32(clean0 + c * 4) != 0;
+            tmem_ld_wait();
+            if (fast) wg_pass_max<16, true>(w, 0, 0, m_scaled, m_raw);
+            else wg_pass_max<16, false>(w, ma0 + c * 64, aa0 + c * 64, m_scaled, m_raw);
+          }
+          float m2 = kFast ? fmaxf(m_scaled, m_raw * c_log2) : m_scaled;
+          {
+            const uint32_t slot = sMax + (((g & 1) * 4) * 128 + row) * 4;
+            sts_f(slot + grp * 128 * 4, m2);
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory");
+#pragma unroll
+            for (int o = 1; o < 4; ++o) m2 = fmaxf(m2, lds_f(slot + ((grp + o) & 3) * 128 * 4));
+          }
+          // P buffer (g&1) was last read by PV(g-2)
+          if (g >= 2) mbar_wait(&o_bar[(g - 2) % 3], ((g - 2) / 3) & 1);
+          const uint32_t pbuf = smem_u32(sP) + (g & 1) * kPPBuf;
+          for (int c = cb; c < ce; ++c) {
+            uint32_t w[16];
+            tmem_ld_32x16(ts + c * 16, w);
+            const bool fast = kFast && lds_u32(clean0 + c * 4) != 0;
+            tmem_ld_wait();
+            sum += fast ? wg_pass_exp<16, true>(w, 0, 0, m2, c_log2, pbuf, row, c * 16)
+                        : wg_pass_exp<16, false>(w, ma0 + c * 64, aa0 + c * 64, m2, c_log2, pbuf, row, c * 16);
+          }
+          sts_f(sSum + (((g & 3) * 4 + grp) * 128 + row) * 4, sum);
+          fence_proxy_async_smem();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_bar[g & 1]);
+          m_blk[kb] = m2;
+          l_own[kb] = sum;
+          // the previous tile's epilogue runs after this tile's first block was handed over
+          if (kb == 0 && t > 0) epilogue(t - 1, g - 2, pm0, pm1, pl0, pl1);
+        }
+        pm0 = m_blk[0]; pm1 = m_blk[1]; pl0 = l_own[0]; pl1 = l_own[1];
+      }
+      epilogue(T - 1, g - 2, pm0, pm1, pl0, pl1);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (is_control) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 int launch_attn_fwd_tail(const void* qkv, long long ld, const uint8_t* mask, void* o, long long ldo,
                          float* lse, int B, int H, int n, float scale_log2, cudaStream_t stream);
 
@@ -1135,11 +1413,12 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
   const int nkb = (q.n + kTile - 1) / kTile;
   static const int variant = [] {
     const char* e = getenv("XCLIP_ATTN_PP_VARIANT");
-    return (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 0;
+    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;
   }();
   XCLIP_REQUIRE(variant < 6 || q.scale_log2 > 0.f, "attn_fwd: the fast-chunk variants need scale > 0");
   // barriers + mask tables + per-row exchange buffers
-  const int tail_bytes = variant >= 4 ? kWgTailBytes : 128 + 2 * 384 * 4 + (4 + 8) * 128 * 4;
+  const int tail_bytes = variant >= 8 ? kPP16TailBytes
+                                      : (variant >= 4 ? kWgTailBytes : 128 + 2 * 384 * 4 + (4 + 8) * 128 * 4);
   const int smem = (1 + 2 * nkb) * kBoxBytes + 2 * kPPBuf + tail_bytes;
   static bool configured = false;
   if (!configured) {
@@ -1160,6 +1439,10 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_wg_kernel<2, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp16_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    XCLIP_CUDA(cudaFuncSetAttribute(attn_fwd_pp16_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   long long grid = num_sms();
@@ -1172,6 +1455,8 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
     case 5: attn_fwd_wg_kernel<2, false><<<(int)grid, 17 * 32, smem, stream>>>(tm, p); break;
     case 6: attn_fwd_wg_kernel<1, true><<<(int)grid, 9 * 32, smem, stream>>>(tm, p); break;
     case 7: attn_fwd_wg_kernel<2, true><<<(int)grid, 17 * 32, smem, stream>>>(tm, p); break;
+    case 8: attn_fwd_pp16_kernel<false><<<(int)grid, kPP16Threads, smem, stream>>>(tm, p); break;
+    case 9: attn_fwd_pp16_kernel<true><<<(int)grid, kPP16Threads, smem, stream>>>(tm, p); break;
     default: attn_fwd_pp_kernel<0><<<(int)grid, kAttnThreads, smem, stream>>>(tm, p); break;
   }
   XCLIP_LAUNCH_CHECK("attn_fwd_pp_kernel");
