@@ -134,6 +134,22 @@ def _gs_worker(rank, world, port, q):
                 w += p.grad / world
         errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
     unused_ok = all(p.grad is None for p in frozen.parameters())
+    # gradient accumulation: the first pass stays local (no_sync), the second one reduces the sum
+    mod.zero_grad(set_to_none=True)
+    d0 = [torch.randn(5, 6, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    d1 = [torch.randn(5, 6, generator=torch.Generator().manual_seed(200 + r)) for r in range(world)]
+    with sync.no_sync():
+        net(d0[rank]).square().sum().backward()
+    net(d1[rank]).square().sum().backward()
+    sync.finish()
+    got = [p.grad.clone() for p in net.parameters()]
+    want = [torch.zeros_like(p) for p in net.parameters()]
+    for r in range(world):
+        ref_net.zero_grad(set_to_none=True)
+        (ref_net(d0[r]).square().sum() + ref_net(d1[r]).square().sum()).backward()
+        for w, p in zip(want, ref_net.parameters()):
+            w += p.grad / world
+    errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
     q.put((rank, nb, max(errs), unused_ok))
     dist.barrier()
     dist.destroy_process_group()
