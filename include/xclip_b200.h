@@ -100,12 +100,14 @@ int xclip_l2norm_bwd(const float* dz, const float* z, const float* inv, void* dp
 int xclip_cast_f32_bf16(const float* src, void* dst, int64_t n, xclip_stream_t stream);
 
 /* ---- fused attention (tcgen05) -------------------------------------------
- * Attention core of x_clip/x_clip.py:217-244 (dim_head = 64, n <= 320, non-causal):
+ * Attention core of x_clip/x_clip.py:217-244 (dim_head = 64, n <= 320).  causal != 0 adds the
+ * reference's causal mask (keys j > i get -FLT_MAX, :233-236); implemented for n <= 128.
  * qkv bf16 [B*n, ld_qkv] holds q | k | v, each heads*64 wide, head-major inside.
  * key_mask uint8 [B, n] (1 = attend; may be NULL).  o bf16 [B*n, ldo] (heads merged).
  * lse f32 [B, heads, n]: base-2 log-sum-exp of scale*log2(e)*scores (saved for backward). */
 int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o, int64_t ldo,
-                   float* lse, int B, int n, int heads, float scale, xclip_stream_t stream);
+                   float* lse, int B, int n, int heads, float scale, int causal,
+                   xclip_stream_t stream);
 /* delta f32 [B, heads, n] is scratch (rowsum(dO*O), written here).  dq_workspace f32
  * [B*n, heads*64] is required when n > 128 (partial dQ across key tiles), else may be NULL;
  * its contents are scratch too (with XCLIP_ATTN_TAIL=1 and n = 128k+1 the first three floats of a
@@ -113,7 +115,7 @@ int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, voi
 int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, const void* o,
                    int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta,
                    void* dqkv, int64_t ld_dqkv, float* dq_workspace, int B, int n, int heads,
-                   float scale, xclip_stream_t stream);
+                   float scale, int causal, xclip_stream_t stream);
 
 /* ---- similarity + InfoNCE / DCL (tcgen05, logits never materialised in forward) ----------
  * Replaces x_clip/x_clip.py:813-847 for one direction of the loss:

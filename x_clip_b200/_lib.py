@@ -48,10 +48,10 @@ SIGNATURES = {
     "xclip_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "xclip_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "xclip_attn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int,
-                               c_int, c_int, c_float, c_void_p]),
+                               c_int, c_int, c_float, c_int, c_void_p]),
     "xclip_attn_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int,
-                               c_int, c_float, c_void_p]),
+                               c_int, c_float, c_int, c_void_p]),
     "xclip_nce_num_col_blocks": (c_int, [c_int]),
     "xclip_nce_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),

@@ -927,13 +927,18 @@ int launch_attn_bwd_tail(const void* qkv, long long ld, const uint8_t* mask, con
 
 }  // namespace xclip
 
+namespace xclip {
+int attn_bwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, const void* d_o,
+                   int64_t lddo, const float* lse, const float* delta, void* dqkv, int64_t ld_dqkv,
+                   int B, int n, int heads, float scale, int causal, cudaStream_t stream);
+}
 using namespace xclip;
 
 extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask,
                               const void* o, int64_t ldo, const void* d_o, int64_t lddo,
                               const float* lse, float* delta, void* dqkv, int64_t ld_dqkv,
                               float* dq_workspace, int B, int n, int heads, float scale,
-                              xclip_stream_t stream) {
+                              int causal, xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
   XCLIP_REQUIRE(qkv && o && d_o && lse && delta && dqkv, "attn_bwd: null pointer");
@@ -959,6 +964,10 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
                                                   delta, B, n, heads);
     XCLIP_LAUNCH_CHECK("attn_delta_kernel");
   }
+  if (n <= kBT)
+    return attn_bwd_small(qkv, ld_qkv, key_mask, d_o, lddo, lse, delta, dqkv, ld_dqkv, B, n, heads,
+                          scale, causal, s);
+  XCLIP_REQUIRE(!causal, "attn_bwd: the causal mask is only implemented for n <= 128 (got n=%d)", n);
 
   AttnBwdParams p;
   p.B = B; p.H = heads; p.n = n;

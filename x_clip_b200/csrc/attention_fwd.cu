@@ -1413,7 +1413,7 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
   const int nkb = (q.n + kTile - 1) / kTile;
   static const int variant = [] {
     const char* e = getenv("XCLIP_ATTN_PP_VARIANT");
-    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;
+    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 7;
   }();
   XCLIP_REQUIRE(variant < 6 || q.scale_log2 > 0.f, "attn_fwd: the fast-chunk variants need scale > 0");
   // barriers + mask tables + per-row exchange buffers
@@ -1467,9 +1467,15 @@ static int launch_attn_fwd_pp(const CUtensorMap& tm, const AttnFwdParams& q, boo
 
 using namespace xclip;
 
+namespace xclip {
+int attn_fwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o, int64_t ldo,
+                   float* lse, int B, int n, int heads, float scale, int causal,
+                   cudaStream_t stream);   // attention_small.cu
+}
+
 extern "C" int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o,
                               int64_t ldo, float* lse, int B, int n, int heads, float scale,
-                              xclip_stream_t stream) {
+                              int causal, xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
   XCLIP_REQUIRE(qkv && o && lse, "attn_fwd: null pointer");
@@ -1480,6 +1486,10 @@ extern "C" int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
   XCLIP_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(o) & 15) == 0,
                 "attn_fwd: misaligned pointer");
+  if (n <= kTile)
+    return attn_fwd_small(qkv, ld_qkv, key_mask, o, ldo, lse, B, n, heads, scale, causal,
+                          reinterpret_cast<cudaStream_t>(stream));
+  XCLIP_REQUIRE(!causal, "attn_fwd: the causal mask is only implemented for n <= 128 (got n=%d)", n);
   AttnFwdParams p;
   p.B = B; p.H = heads; p.n = n;
   p.nkp = (n + 15) / 16 * 16;

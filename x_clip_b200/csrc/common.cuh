@@ -32,16 +32,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
-// Single-thread regions that issue tcgen05.mma / TMA instructions.  `lane == 0` leaves ptxas
-// unable to prove that one thread is active, so every UTCHMMA / UTMALDG gets a waterfall loop
-// (ELECT + BRA.U.ANY) and R2UR moves: ~17 SASS instructions per MMA instead of ~8.  Building with
-// XCLIP_BUILD_ELECT=1 (-DXCLIP_USE_ELECT) switches those regions to elect.sync; the default stays
-// `lane == 0` until the elect build has passed the GPU suite.
-#ifdef XCLIP_USE_ELECT
+// Single-thread regions that issue tcgen05.mma / TMA instructions are entered through
+// elect.sync: with `lane == 0` ptxas cannot prove that one thread is active, so every UTCHMMA /
+// UTMALDG got a waterfall loop (ELECT + BRA.U.ANY + R2UR, ~17 SASS instructions per MMA instead
+// of ~8).  Validated on a B200 in round 2 (full GPU suite; attention backward 1.91 -> 1.80 ms).
 #define XCLIP_ONE_LANE(lane) (::xclip::elect_one())
-#else
-#define XCLIP_ONE_LANE(lane) ((lane) == 0)
-#endif
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

@@ -210,7 +210,7 @@ def l2norm_bwd(dz, z, inv):
     return dp
 
 
-def attn_fwd(qkv, key_mask, B, n, heads, scale):
+def attn_fwd(qkv, key_mask, B, n, heads, scale, causal=False):
     """qkv bf16 [B*n, 3*heads*64] -> (o bf16 [B*n, heads*64], lse f32 [B, heads, n])."""
     _need(qkv, BF16, "qkv"); _rows2d(qkv, "qkv")
     o = torch.empty((B * n, heads * 64), device=qkv.device, dtype=BF16)
@@ -219,18 +219,19 @@ def attn_fwd(qkv, key_mask, B, n, heads, scale):
         if key_mask.dtype != torch.bool or tuple(key_mask.shape) != (B, n) or not key_mask.is_contiguous():
             raise _lib.XClipB200Error("attn_fwd: key_mask must be a contiguous bool [B, n]")
     _call("attn_fwd", 4.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 4, "xclip_attn_fwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
-              o.stride(0), lse.data_ptr(), B, n, heads, float(scale), _stream())
+              o.stride(0), lse.data_ptr(), B, n, heads, float(scale), 1 if causal else 0, _stream())
     return o, lse
 
 
-def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale):
+def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale, causal=False):
     _need(d_o, BF16, "d_o"); _rows2d(d_o, "d_o")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, heads, n), device=qkv.device, dtype=F32)
     ws = torch.empty((B * n, heads * 64), device=qkv.device, dtype=F32) if n > 128 else None
     _call("attn_bwd", 10.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 8, "xclip_attn_bwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
               o.stride(0), d_o.data_ptr(), d_o.stride(0), lse.data_ptr(), delta.data_ptr(),
-              dqkv.data_ptr(), dqkv.stride(0), _ptr(ws), B, n, heads, float(scale), _stream())
+              dqkv.data_ptr(), dqkv.stride(0), _ptr(ws), B, n, heads, float(scale),
+              1 if causal else 0, _stream())
     return dqkv
 
 
