@@ -150,7 +150,56 @@ def _gs_worker(rank, world, port, q):
         for w, p in zip(want, ref_net.parameters()):
             w += p.grad / world
     errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
-    q.put((rank, nb, max(errs), unused_ok))
+
+    # micro-batched backward (engine.ChunkedClipLossFn pattern): one autograd pass per chunk INSIDE
+    # a backward; every pass but the last defers the hooks, so each bucket is reduced once, with
+    # the gradient accumulated over all chunks (first-chunk-only reduction)
+    class Chunked(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, defer):
+            ctx.x, ctx.defer = x, defer
+            with torch.no_grad():
+                return sum(net(c).square().sum() for c in x.chunk(3))
+
+        @staticmethod
+        def backward(ctx, g):
+            chunks = ctx.x.chunk(3)
+            for k, c in enumerate(chunks):
+                with torch.enable_grad(), D.defer_grad_sync(ctx.defer and k != len(chunks) - 1):
+                    torch.autograd.backward(net(c).square().sum(), g)
+            return None, None
+
+    dch = [torch.randn(6, 6, generator=torch.Generator().manual_seed(300 + r)) for r in range(world)]
+    mod.zero_grad(set_to_none=True)
+    Chunked.apply(dch[rank].requires_grad_(True), True).backward()
+    sync.finish()
+    got = [p.grad.clone() for p in net.parameters()]
+    want = [torch.zeros_like(p) for p in net.parameters()]
+    for r in range(world):
+        ref_net.zero_grad(set_to_none=True)
+        ref_net(dch[r].detach()).square().sum().backward()
+        for w, p in zip(want, ref_net.parameters()):
+            w += p.grad / world
+    errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
+    # without the deferral the second arrival of a parameter is an error, not a silent wrong result
+    mod.zero_grad(set_to_none=True)
+    raised = False
+    try:
+        Chunked.apply(dch[rank].requires_grad_(True), False).backward()
+    except RuntimeError as e:
+        raised = "second gradient" in str(e)
+    for b in sync._buckets:                       # drain whatever the failed pass launched
+        if b["work"] is not None:
+            b["work"].wait()
+        b["arrived"], b["work"], b["flat"], b["members"] = 0, None, None, None
+    # unequal local batches are reported, not hung on
+    uneq = False
+    try:
+        D.assert_equal_local_batch(3 + rank, torch.device("cpu"))
+    except RuntimeError:
+        uneq = True
+    D.assert_equal_local_batch(3, torch.device("cpu"))
+    q.put((rank, nb, max(errs), unused_ok and raised and uneq))
     dist.barrier()
     dist.destroy_process_group()
 

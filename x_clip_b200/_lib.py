@@ -11,9 +11,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_void_p
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-# XCLIP_LIB_VARIANT=elect loads the experimental build made with XCLIP_BUILD_ELECT=1 (build.py)
-_VARIANT = os.environ.get("XCLIP_LIB_VARIANT", "")
-LIB_PATH = _PKG / (f"libxclip_b200_{_VARIANT}.so" if _VARIANT else "libxclip_b200.so")
+LIB_PATH = _PKG / "libxclip_b200.so"
 
 _lib = None
 

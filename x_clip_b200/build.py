@@ -5,6 +5,7 @@ without a GPU; the resulting .so is git-ignored but travels with the source tree
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -14,11 +15,8 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-# XCLIP_BUILD_ELECT=1 builds the experimental elect.sync variant NEXT TO the default library
-# (own object directory, libxclip_b200_elect.so); `XCLIP_LIB_VARIANT=elect` makes _lib.py load it.
-_VARIANT = "elect" if os.environ.get("XCLIP_BUILD_ELECT") == "1" else ""
-OBJ = PKG / "csrc" / ("build_" + _VARIANT if _VARIANT else "build")
-LIB = PKG / ("libxclip_b200_" + _VARIANT + ".so" if _VARIANT else "libxclip_b200.so")
+OBJ = PKG / "csrc" / "build"
+LIB = PKG / "libxclip_b200.so"
 
 NVCC_FLAGS = [
     "-O3",
@@ -30,14 +28,6 @@ NVCC_FLAGS = [
 ]
 
 
-def _extra_flags() -> list:
-    """Opt-in code-generation switches (see csrc/common.cuh); empty for the default build."""
-    flags = []
-    if os.environ.get("XCLIP_BUILD_ELECT") == "1":
-        flags.append("-DXCLIP_USE_ELECT=1")
-    return flags
-
-
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
         if cand and Path(cand).exists():
@@ -45,17 +35,34 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: x_clip_b200 has no prebuilt or fallback path")
 
 
-def _newest_header_mtime() -> float:
-    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "xclip_b200.h"]
-    return max(h.stat().st_mtime for h in hdrs)
+def _headers_digest() -> bytes:
+    """sha256 over every header a translation unit may include (contents, not mtimes)."""
+    h = hashlib.sha256()
+    hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "xclip_b200.h"]
+    for f in hdrs:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.digest()
 
 
-def _compile(src: Path, verbose: bool) -> Path:
+def _source_key(src: Path, hdr_digest: bytes) -> str:
+    """Content hash that decides whether an object file is current: source + headers + flags +
+    compiler.  (mtimes say nothing on a box that received the tree as a snapshot.)"""
+    h = hashlib.sha256()
+    h.update(src.read_bytes())
+    h.update(hdr_digest)
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(_nvcc().encode())
+    return h.hexdigest()
+
+
+def _compile(src: Path, verbose: bool, hdr_digest: bytes) -> tuple:
     obj = OBJ / (src.stem + ".o")
-    dep_m = max(src.stat().st_mtime, _newest_header_mtime())
-    if obj.exists() and obj.stat().st_mtime > dep_m:
-        return obj
-    cmd = [_nvcc(), *NVCC_FLAGS, *_extra_flags(), "-c", str(src), "-o", str(obj)]
+    stamp = OBJ / (src.stem + ".sha256")
+    key = _source_key(src, hdr_digest)
+    if obj.exists() and stamp.exists() and stamp.read_text().strip() == key and not verbose:
+        return obj, key, False
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -64,26 +71,34 @@ def _compile(src: Path, verbose: bool) -> Path:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
     if verbose and r.stderr:
         print(r.stderr)
-    return obj
+    stamp.write_text(key)
+    return obj, key, True
 
 
 def build(verbose: bool = False, force: bool = False) -> Path:
+    """Compile every csrc/*.cu whose content hash changed and relink when the set of object
+    hashes differs from the one recorded next to the library."""
     OBJ.mkdir(parents=True, exist_ok=True)
     if force:
-        for o in OBJ.glob("*.o"):
+        for o in list(OBJ.glob("*.o")) + list(OBJ.glob("*.sha256")):
             o.unlink()
     srcs = sorted(CSRC.glob("*.cu"))
     if not srcs:
         raise RuntimeError("no CUDA sources found")
+    hdr = _headers_digest()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    if LIB.exists() and all(LIB.stat().st_mtime > o.stat().st_mtime for o in objs):
+        res = list(ex.map(lambda s: _compile(s, verbose, hdr), srcs))
+    objs = [r[0] for r in res]
+    link_key = hashlib.sha256("\n".join(f"{o.name}:{k}" for o, k, _ in res).encode()).hexdigest()
+    stamp = OBJ / "link.sha256"
+    if LIB.exists() and stamp.exists() and stamp.read_text().strip() == link_key:
         return LIB
     cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs),
            "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    stamp.write_text(link_key)
     return LIB
 
 

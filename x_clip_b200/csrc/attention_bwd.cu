@@ -43,13 +43,7 @@ struct AttnBwdParams {
   bf16* dqkv;            // [B*n, ld] q | k | v gradients
   long long ld;
   float* dq_ws;          // fp32 [B*n, H*64] or null when n <= 128
-  // Tail mode (n = 128k+1, see attention_tail.cu): tiles cover the tokens [0, nt) with nt = n-1;
-  // token z = n-1 was handled by attn_bwd_tail_kernel, which left (ds^c_t, ds^r_t, p^r_t) in the
-  // first three floats of token t's dq_ws slot.  The epilogues add the rank-1 terms
-  // dQ_t += ds^c_t k_z, dK_t += ds^r_t q_z, dV_t += p^r_t dO_z.
-  int nt, tail;
-  const bf16* qkv; long long ld_qkv;
-  const bf16* d_o; long long lddo;
+  int nt;                // == n (kept as a separate name: tokens covered by the tiles)
 };
 
 __device__ __forceinline__ float bwd_ex2(float x) {
@@ -129,8 +123,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
   const uint32_t sLse = sAdd + 128 * 4;        // [384] f32: log-sum-exp of every query of this (b,h)
   const uint32_t sDelta = sLse + 384 * 4;      // [384] f32
-  const uint32_t sTail = sDelta + 384 * 4;     // [3][384] f32: ds^c, ds^r, p^r of every token (tail mode)
-  const uint32_t sVec = sTail + 3 * 384 * 4;   // [3][64] f32: k_z, q_z, dO_z (tail mode)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -299,8 +291,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
       const int b = bh / p.H, h = bh % p.H;
       for (int j = 0; j < ntiles; ++j) {
-        // tail mode: the previous item's last dK/dV epilogue reads sTail / sVec
-        if (p.tail && j == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
         // key-tile tables (all compute threads are past every read of the previous tables:
         // the last read precedes their pds arrive of the previous pair, and bar.sync orders)
         if (threadIdx.x < kBT) {
@@ -315,26 +305,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const long long s_idx = ((long long)b * p.H + h) * p.n + q;
             bwd_sts_f(sLse + q * 4, q < p.nt ? p.lse[s_idx] : INFINITY);
             bwd_sts_f(sDelta + q * 4, q < p.nt ? p.delta[s_idx] : 0.f);
-          }
-          if (p.tail) {
-            for (int q = threadIdx.x; q < 384; q += kBwdComputeWarps * 32) {
-              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-              if (q < p.nt) {
-                const float* w = p.dq_ws + ((long long)b * p.n + q) * inner + h * kBDh;
-                c0 = w[0]; c1 = w[1]; c2 = w[2];
-              }
-              bwd_sts_f(sTail + q * 4, c0);
-              bwd_sts_f(sTail + (384 + q) * 4, c1);
-              bwd_sts_f(sTail + (768 + q) * 4, c2);
-            }
-            if (threadIdx.x < 192) {
-              const int which = threadIdx.x >> 6, d = threadIdx.x & 63;
-              const long long z = (long long)b * p.n + (p.n - 1);
-              const bf16 x = which == 0   ? p.qkv[z * p.ld_qkv + inner + h * kBDh + d]     // k_z
-                             : which == 1 ? p.qkv[z * p.ld_qkv + h * kBDh + d]             // q_z
-                                          : p.d_o[z * p.lddo + h * kBDh + d];              // dO_z
-              bwd_sts_f(sVec + threadIdx.x * 4, __bfloat162float(x));
-            }
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -430,16 +400,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 for (int e = 0; e < 32; e += 4)
                   *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
               } else {
-                if (p.tail) {   // + ds^c_i k_z
-                  float cds;
-                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cds) : "r"(sTail + q_idx * 4));
-#pragma unroll
-                  for (int e = 0; e < 32; e += 4) {
-                    const float4 kz = bwd_lds_f4(sVec + (half * 32 + e) * 4);
-                    f[e] = fmaf(cds, kz.x, f[e]); f[e + 1] = fmaf(cds, kz.y, f[e + 1]);
-                    f[e + 2] = fmaf(cds, kz.z, f[e + 2]); f[e + 3] = fmaf(cds, kz.w, f[e + 3]);
-                  }
-                }
                 bf16* dst = p.dqkv + tok * p.ld + h * kBDh + half * 32;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8) {
@@ -466,21 +426,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             uint32_t v[32];
             tmem_ld_32x32((half == 0 ? tdK : tdV) + lane_off + c * 32, v);
             tmem_ld_wait();
-            if (p.tail && key < p.nt) {   // dK: + ds^r_key q_z   dV: + p^r_key dO_z
-              float coef;
-              asm volatile("ld.shared.f32 %0, [%1];"
-                           : "=f"(coef)
-                           : "r"(sTail + ((half == 0 ? 384 : 768) + key) * 4));
-              const uint32_t vec = sVec + ((half == 0 ? 64 : 128) + c * 32) * 4;
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                const float4 x = bwd_lds_f4(vec + e * 4);
-                v[e] = __float_as_uint(fmaf(coef, x.x, __uint_as_float(v[e])));
-                v[e + 1] = __float_as_uint(fmaf(coef, x.y, __uint_as_float(v[e + 1])));
-                v[e + 2] = __float_as_uint(fmaf(coef, x.z, __uint_as_float(v[e + 2])));
-                v[e + 3] = __float_as_uint(fmaf(coef, x.w, __uint_as_float(v[e + 3])));
-              }
-            }
             if (key < p.nt) {
               bf16* dst = p.dqkv + ((long long)b * p.n + key) * p.ld + (half + 1) * inner +
                           h * kBDh + c * 32;
@@ -508,422 +453,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tmem_dealloc<512>(tmem_base);
   }
 }
-
-// ---------------------------------------------------------------------------------------------
-// 16-compute-warp variant (XCLIP_ATTN_BWD16=1, experimental - DESIGN.md section 9).  Same
-// protocol, TMEM / smem plan and issue thread as attn_bwd_kernel; four warps instead of two share
-// a query row (32 key columns each, handled as two 16-column steps to stay under the 96-register
-// cap of a 544-thread CTA), so four warps per scheduler hide the TMEM / MUFU / shared-memory
-// latencies of the P, dS computation and the per-pair serial chain shortens.  The body below is
-// the validated kernel with the thread mapping changed - keep the two in sync.
-constexpr int kBwd16ComputeWarps = 16;
-constexpr int kBwd16Threads = (kBwd16ComputeWarps + 1) * 32;
-
-__global__ void __launch_bounds__(kBwd16Threads, 1)
-attn_bwd16_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const AttnBwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sKV = smem;                  // 2 buffers x (K box, V box)
-  uint8_t* sQdO = sKV + 4 * kBBox;      // 2 buffers x (Q box, dO box)
-  uint8_t* sP = sQdO + 4 * kBBox;       // 2 blocks of [128 x 64] bf16
-  uint8_t* sdS = sP + 2 * kBBox;        // 2 blocks
-  uint8_t* tail = sdS + 2 * kBBox;
-  uint64_t* kv_bar = reinterpret_cast<uint64_t*>(tail);  // [2]
-  uint64_t* qdo_bar = kv_bar + 2;                        // [2]
-  uint64_t* s_bar = kv_bar + 4;
-  uint64_t* pds_bar = kv_bar + 5;
-  uint64_t* g_bar = kv_bar + 6;
-  uint64_t* dq_bar = kv_bar + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_bar + 8);
-  const uint32_t sMul = smem_u32(tail + 128);  // [128] f32: scale*log2e for attendable keys, else 0
-  const uint32_t sAdd = sMul + 128 * 4;        // [128] f32: 0 or -inf (masked / beyond n)
-  const uint32_t sLse = sAdd + 128 * 4;        // [384] f32: log-sum-exp of every query of this (b,h)
-  const uint32_t sDelta = sLse + 384 * 4;      // [384] f32
-  const uint32_t sTail = sDelta + 384 * 4;     // [3][384] f32: ds^c, ds^r, p^r of every token (tail mode)
-  const uint32_t sVec = sTail + 3 * 384 * 4;   // [3][64] f32: k_z, q_z, dO_z (tail mode)
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const bool is_control = warp == kBwd16ComputeWarps;
-
-  if (threadIdx.x == 0) {
-    if ((smem_u32(smem) & 1023u) != 0) {
-      printf("xclip attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
-      __trap();
-    }
-    mbar_init(&kv_bar[0], 1);
-    mbar_init(&kv_bar[1], 1);
-    mbar_init(&qdo_bar[0], 1);
-    mbar_init(&qdo_bar[1], 1);
-    mbar_init(s_bar, 1);
-    mbar_init(pds_bar, kBwd16ComputeWarps);
-    mbar_init(g_bar, 1);
-    mbar_init(dq_bar, 1);
-    fence_barrier_init();
-  }
-  if (is_control) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      tma_prefetch_desc(&tm_do);
-    }
-    tmem_alloc<512>(tmem_slot);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256,
-                 tdK = tmem_base + 320, tdQ = tmem_base + 384;
-
-  const int ntiles = (p.nt + kBT - 1) / kBT;
-  const int pairs_per_bh = ntiles * ntiles;
-  const int inner = p.H * kBDh;
-  const int num_bh = p.B * p.H;
-  // this CTA's work: bh = blockIdx.x + k*gridDim.x, k = 0..my_bh-1; linear pair index pc
-  const int my_bh = (num_bh - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int my_pairs = my_bh * pairs_per_bh;
-
-  if (is_control) {
-    // ===================== control warp =====================
-    if (XCLIP_ONE_LANE(lane)) {
-      // Coordinates of a pair are tracked incrementally (no divisions on this single-thread
-      // critical path): `cur` is the pair whose gradient MMAs are issued, `nxt` the one whose
-      // tiles are prefetched / whose S,dP are issued, `kvn` the next key step to prefetch.
-      struct Coord { int bh, j, i; };
-      auto advance = [&](Coord& c) {
-        if (++c.i == ntiles) { c.i = 0; if (++c.j == ntiles) { c.j = 0; c.bh += gridDim.x; } }
-      };
-      auto load_kv = [&](const Coord& c, int kc) {
-        const int b = c.bh / p.H, h = c.bh - b * p.H;
-        uint8_t* dst = sKV + (kc & 1) * 2 * kBBox;
-        mbar_arrive_expect_tx(&kv_bar[kc & 1], 2 * kBBox);
-        tma_load_3d(dst, &tm_qkv, &kv_bar[kc & 1], inner + h * kBDh, c.j * kBT, b);
-        tma_load_3d(dst + kBBox, &tm_qkv, &kv_bar[kc & 1], 2 * inner + h * kBDh, c.j * kBT, b);
-      };
-      auto load_qdo = [&](const Coord& c, int pc) {
-        const int b = c.bh / p.H, h = c.bh - b * p.H;
-        uint8_t* dst = sQdO + (pc & 1) * 2 * kBBox;
-        mbar_arrive_expect_tx(&qdo_bar[pc & 1], 2 * kBBox);
-        tma_load_3d(dst, &tm_qkv, &qdo_bar[pc & 1], h * kBDh, c.i * kBT, b);
-        tma_load_3d(dst + kBBox, &tm_do, &qdo_bar[pc & 1], h * kBDh, c.i * kBT, b);
-      };
-      const uint32_t sKV_a = smem_u32(sKV), sQdO_a = smem_u32(sQdO);
-      // descriptors whose operand never moves: P^T / dS^T (MN-major A) and dS (K-major A)
-      const uint64_t desc_pT = make_smem_desc(smem_u32(sP), kBBox, 1024);
-      const uint64_t desc_dsT = make_smem_desc(smem_u32(sdS), kBBox, 1024);
-      const uint64_t desc_dsK = make_smem_desc(smem_u32(sdS), 0, 1024);
-      auto issue_scores = [&](const Coord& c, int pc, int kc) {  // S and dP of pair pc
-        // only the key columns that exist (rounded to 32) are produced for a partial key tile
-        const int vc = min(kBT, (p.nt - c.j * kBT + 31) / 32 * 32);
-        const uint32_t idesc = make_idesc_bf16(kBT, vc, kMajorK, kMajorK);
-        const uint32_t kv = sKV_a + (kc & 1) * 2 * kBBox;
-        const uint32_t qd_ = sQdO_a + (pc & 1) * 2 * kBBox;
-        const uint64_t qd = make_smem_desc(qd_, 0, 1024);
-        const uint64_t kd = make_smem_desc(kv, 0, 1024);
-        const uint64_t dod = make_smem_desc(qd_ + kBBox, 0, 1024);
-        const uint64_t vd = make_smem_desc(kv + kBBox, 0, 1024);
-#pragma unroll
-        for (int k = 0; k < kBDh / 16; ++k) umma_bf16(tS, qd + 2 * k, kd + 2 * k, idesc, k > 0);
-#pragma unroll
-        for (int k = 0; k < kBDh / 16; ++k) umma_bf16(tdP, dod + 2 * k, vd + 2 * k, idesc, k > 0);
-        umma_commit(s_bar);
-      };
-
-      Coord cur{(int)blockIdx.x, 0, 0}, nxt = cur, kvn = cur;
-      if (my_pairs > 0) {
-        load_kv(cur, 0);
-        load_qdo(cur, 0);
-        mbar_wait(&kv_bar[0], 0);
-        mbar_wait(&qdo_bar[0], 0);
-        tcgen05_fence_after();
-        issue_scores(cur, 0, 0);
-        advance(nxt);
-        kvn.j = 1;
-        if (kvn.j == ntiles) { kvn.j = 0; kvn.bh += gridDim.x; }
-      }
-      int kc = 0;                       // running key-step id of `cur`
-      for (int pc = 0; pc < my_pairs; ++pc) {
-        const int i = cur.i, j = cur.j;
-        const int ksteps_q = min(kBT, (p.nt - i * kBT + 15) / 16 * 16) / 16;   // valid query groups
-        const int ksteps_k = min(kBT, (p.nt - j * kBT + 31) / 32 * 32) / 16;   // valid key groups
-        const bool has_next = pc + 1 < my_pairs;
-        // all MMAs of pair pc-1 retired: its Q/dO buffer and (if it closed a key step) the
-        // K/V buffer of that step may be overwritten
-        if (pc >= 1) mbar_wait(g_bar, (pc - 1) & 1);
-        if (i == 0 && (kc + 1) * ntiles < my_pairs) {   // prefetch K/V of the next key step
-          load_kv(kvn, kc + 1);
-          if (++kvn.j == ntiles) { kvn.j = 0; kvn.bh += gridDim.x; }
-        }
-        if (has_next) load_qdo(nxt, pc + 1);
-
-        mbar_wait(pds_bar, pc & 1);   // P, dS of pair pc are in smem; S/dP TMEM consumed
-        tcgen05_fence_after();
-        {
-          constexpr uint32_t idesc_t = make_idesc_bf16(kBT, kBDh, kMajorMN, kMajorMN);
-          constexpr uint32_t idesc_q = make_idesc_bf16(kBT, kBDh, kMajorK, kMajorMN);
-          const uint32_t kv = sKV_a + (kc & 1) * 2 * kBBox;
-          const uint32_t qd_ = sQdO_a + (pc & 1) * 2 * kBBox;
-          const uint64_t desc_kmn = make_smem_desc(kv, 8192, 1024);          // K_j, MN-major B
-          const uint64_t desc_qmn = make_smem_desc(qd_, 8192, 1024);         // Q_i, MN-major B
-          const uint64_t desc_domn = make_smem_desc(qd_ + kBBox, 8192, 1024);  // dO_i, MN-major B
-          // dQ first (contraction over the valid keys): its epilogue overlaps the dV/dK MMAs.
-          // Fully unrolled with compile-time offsets; descriptor address units are 16 bytes.
-#pragma unroll
-          for (int k = 0; k < kBT / 16; ++k) {
-            if (k < ksteps_k)
-              umma_bf16(tdQ, desc_dsK + ((k >> 2) * (kBBox >> 4) + (k & 3) * 2),
-                        desc_kmn + k * 128, idesc_q, k > 0 ? 1u : 0u);
-          }
-          umma_commit(dq_bar);
-#pragma unroll
-          for (int k = 0; k < kBT / 16; ++k) {   // contraction over the valid queries
-            if (k < ksteps_q) {
-              umma_bf16(tdV, desc_pT + k * 128, desc_domn + k * 128, idesc_t,
-                        (i > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(tdK, desc_dsT + k * 128, desc_qmn + k * 128, idesc_t,
-                        (i > 0 || k > 0) ? 1u : 0u);
-            }
-          }
-        }
-        umma_commit(g_bar);
-        if (has_next) {               // S/dP of the next pair queue right behind
-          const int nkc = (nxt.i == 0) ? kc + 1 : kc;
-          if (nxt.i == 0) mbar_wait(&kv_bar[nkc & 1], (nkc >> 1) & 1);
-          mbar_wait(&qdo_bar[(pc + 1) & 1], ((pc + 1) >> 1) & 1);
-          tcgen05_fence_after();
-          issue_scores(nxt, pc + 1, nkc);
-        }
-        advance(cur);
-        advance(nxt);
-        if (cur.i == 0) ++kc;
-      }
-      if (my_pairs > 0) mbar_wait(g_bar, (my_pairs - 1) & 1);
-    }
-    __syncwarp();
-  } else {
-    // ===================== compute warps =====================
-    const int quarter = warp & 3, grp = warp >> 2;   // 4 column groups share a row
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    int pc = 0;
-    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
-      const int b = bh / p.H, h = bh % p.H;
-      for (int j = 0; j < ntiles; ++j) {
-        // tail mode: the previous item's last dK/dV epilogue reads sTail / sVec
-        if (p.tail && j == 0) asm volatile("bar.sync 1, 512;" ::: "memory");
-        // key-tile tables (all compute threads are past every read of the previous tables:
-        // the last read precedes their pds arrive of the previous pair, and bar.sync orders)
-        if (threadIdx.x < kBT) {
-          const int key = j * kBT + threadIdx.x;
-          const bool keep =
-              key < p.nt && (p.mask ? (p.mask[(long long)b * p.n + key] != 0) : true);
-          bwd_sts_f(sMul + threadIdx.x * 4, keep ? p.scale_log2 : 0.f);
-          bwd_sts_f(sAdd + threadIdx.x * 4, keep ? 0.f : -INFINITY);
-        }
-        if (j == 0) {   // per-(b,h) row statistics: +inf lse -> p = 0 for rows beyond n
-          for (int q = threadIdx.x; q < 384; q += kBwd16ComputeWarps * 32) {
-            const long long s_idx = ((long long)b * p.H + h) * p.n + q;
-            bwd_sts_f(sLse + q * 4, q < p.nt ? p.lse[s_idx] : INFINITY);
-            bwd_sts_f(sDelta + q * 4, q < p.nt ? p.delta[s_idx] : 0.f);
-          }
-          if (p.tail) {
-            for (int q = threadIdx.x; q < 384; q += kBwd16ComputeWarps * 32) {
-              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-              if (q < p.nt) {
-                const float* w = p.dq_ws + ((long long)b * p.n + q) * inner + h * kBDh;
-                c0 = w[0]; c1 = w[1]; c2 = w[2];
-              }
-              bwd_sts_f(sTail + q * 4, c0);
-              bwd_sts_f(sTail + (384 + q) * 4, c1);
-              bwd_sts_f(sTail + (768 + q) * 4, c2);
-            }
-            if (threadIdx.x < 192) {
-              const int which = threadIdx.x >> 6, d = threadIdx.x & 63;
-              const long long z = (long long)b * p.n + (p.n - 1);
-              const bf16 x = which == 0   ? p.qkv[z * p.ld_qkv + inner + h * kBDh + d]     // k_z
-                             : which == 1 ? p.qkv[z * p.ld_qkv + h * kBDh + d]             // q_z
-                                          : p.d_o[z * p.lddo + h * kBDh + d];              // dO_z
-              bwd_sts_f(sVec + threadIdx.x * 4, __bfloat162float(x));
-            }
-          }
-        }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-
-        for (int i = 0; i < ntiles; ++i, ++pc) {
-          const int q_idx = i * kBT + row;
-          const bool q_ok = q_idx < p.nt;
-          float lse_i, delta_i;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lse_i) : "r"(sLse + q_idx * 4));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(delta_i) : "r"(sDelta + q_idx * 4));
-          mbar_wait(s_bar, pc & 1);
-          tcgen05_fence_after();
-          // P/dS smem of the previous pair is still read by its dV/dK MMAs until g_bar fires
-          if (pc >= 1) mbar_wait(g_bar, (pc - 1) & 1);
-          // Partial tiles: the MMAs only touch query groups < vr16 and key columns < vc32 (see the
-          // control warp), and every output row depends on its own operand row only, so warps /
-          // chunks that are pure padding skip their math and leave their smem slots untouched.
-          const int vr16 = min(kBT, (p.nt - i * kBT + 15) / 16 * 16);
-          const int vc32 = min(kBT, (p.nt - j * kBT + 31) / 32 * 32);
-          const bool warp_alive = quarter * 32 < vr16;
-#pragma unroll
-          for (int cc0 = 0; cc0 < 2; ++cc0) {
-            const int c0 = grp * 32 + cc0 * 16;
-            if (!warp_alive || c0 >= vc32) continue;
-            uint32_t sv[16], dv[16];
-            tmem_ld_32x16(tS + lane_off + c0, sv);
-            tmem_ld_32x16(tdP + lane_off + c0, dv);
-            tmem_ld_wait();
-            float pr[16], ds[16];
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 m = bwd_lds_f4(sMul + (c0 + e) * 4);
-              const float4 a = bwd_lds_f4(sAdd + (c0 + e) * 4);
-              const float mm[4] = {m.x, m.y, m.z, m.w}, aa[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float t = fmaf(__uint_as_float(sv[e + u]), mm[u], aa[u]);
-                const float pv = bwd_ex2(t - lse_i);
-                pr[e + u] = pv;
-                ds[e + u] = pv * (__uint_as_float(dv[e + u]) - delta_i) * p.scale;
-              }
-            }
-            const uint32_t pblk = smem_u32(sP) + (c0 >> 6) * kBBox;
-            const uint32_t dblk = smem_u32(sdS) + (c0 >> 6) * kBBox;
-            const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              bwd_sts_v4(pblk + swz128(row, chunk0 + cc),
-                         pack_bf16x2(pr[cc * 8 + 0], pr[cc * 8 + 1]),
-                         pack_bf16x2(pr[cc * 8 + 2], pr[cc * 8 + 3]),
-                         pack_bf16x2(pr[cc * 8 + 4], pr[cc * 8 + 5]),
-                         pack_bf16x2(pr[cc * 8 + 6], pr[cc * 8 + 7]));
-              bwd_sts_v4(dblk + swz128(row, chunk0 + cc),
-                         pack_bf16x2(ds[cc * 8 + 0], ds[cc * 8 + 1]),
-                         pack_bf16x2(ds[cc * 8 + 2], ds[cc * 8 + 3]),
-                         pack_bf16x2(ds[cc * 8 + 4], ds[cc * 8 + 5]),
-                         pack_bf16x2(ds[cc * 8 + 6], ds[cc * 8 + 7]));
-            }
-          }
-          fence_proxy_async_smem();
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pds_bar);
-
-          // dQ_i partial for this key tile: this thread owns 16 of the 64 columns of its row.
-          // The fp32 partial of the previous key tiles is fetched BEFORE waiting for the MMAs.
-          const long long tok = (long long)b * p.n + (q_ok ? q_idx : 0);
-          float* ws = p.dq_ws ? p.dq_ws + tok * inner + h * kBDh + grp * 16 : nullptr;
-          float4 prev[4];
-          if (j > 0 && q_ok) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) prev[e] = *reinterpret_cast<const float4*>(ws + e * 4);
-          }
-          mbar_wait(dq_bar, pc & 1);
-          tcgen05_fence_after();
-          {
-            uint32_t v[16];
-            tmem_ld_32x16(tdQ + lane_off + grp * 16, v);
-            tmem_ld_wait();
-            if (q_ok) {
-              float f[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
-              if (j > 0) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[e * 4] += prev[e].x; f[e * 4 + 1] += prev[e].y;
-                  f[e * 4 + 2] += prev[e].z; f[e * 4 + 3] += prev[e].w;
-                }
-              }
-              if (j < ntiles - 1) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                  *reinterpret_cast<float4*>(ws + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-              } else {
-                if (p.tail) {   // + ds^c_i k_z
-                  float cds;
-                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cds) : "r"(sTail + q_idx * 4));
-#pragma unroll
-                  for (int e = 0; e < 16; e += 4) {
-                    const float4 kz = bwd_lds_f4(sVec + (grp * 16 + e) * 4);
-                    f[e] = fmaf(cds, kz.x, f[e]); f[e + 1] = fmaf(cds, kz.y, f[e + 1]);
-                    f[e + 2] = fmaf(cds, kz.z, f[e + 2]); f[e + 3] = fmaf(cds, kz.w, f[e + 3]);
-                  }
-                }
-                bf16* dst = p.dqkv + tok * p.ld + h * kBDh + grp * 16;
-#pragma unroll
-                for (int e = 0; e < 16; e += 8) {
-                  uint4 o;
-                  o.x = pack_bf16x2(f[e], f[e + 1]);
-                  o.y = pack_bf16x2(f[e + 2], f[e + 3]);
-                  o.z = pack_bf16x2(f[e + 4], f[e + 5]);
-                  o.w = pack_bf16x2(f[e + 6], f[e + 7]);
-                  *reinterpret_cast<uint4*>(dst + e) = o;
-                }
-              }
-            }
-          }
-          tcgen05_fence_before();
-        }  // i
-
-        // dK_j (groups 0,1) / dV_j (groups 2,3), 32 columns each, are complete once the last
-        // pair's dV/dK MMAs retired
-        {
-          const int key = j * kBT + row;
-          const int half = grp >> 1, c = grp & 1;
-          mbar_wait(g_bar, (pc - 1) & 1);
-          tcgen05_fence_after();
-          {
-            uint32_t v[32];
-            tmem_ld_32x32((half == 0 ? tdK : tdV) + lane_off + c * 32, v);
-            tmem_ld_wait();
-            if (p.tail && key < p.nt) {   // dK: + ds^r_key q_z   dV: + p^r_key dO_z
-              float coef;
-              asm volatile("ld.shared.f32 %0, [%1];"
-                           : "=f"(coef)
-                           : "r"(sTail + ((half == 0 ? 384 : 768) + key) * 4));
-              const uint32_t vec = sVec + ((half == 0 ? 64 : 128) + c * 32) * 4;
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                const float4 x = bwd_lds_f4(vec + e * 4);
-                v[e] = __float_as_uint(fmaf(coef, x.x, __uint_as_float(v[e])));
-                v[e + 1] = __float_as_uint(fmaf(coef, x.y, __uint_as_float(v[e + 1])));
-                v[e + 2] = __float_as_uint(fmaf(coef, x.z, __uint_as_float(v[e + 2])));
-                v[e + 3] = __float_as_uint(fmaf(coef, x.w, __uint_as_float(v[e + 3])));
-              }
-            }
-            if (key < p.nt) {
-              bf16* dst = p.dqkv + ((long long)b * p.n + key) * p.ld + (half + 1) * inner +
-                          h * kBDh + c * 32;
-#pragma unroll
-              for (int e = 0; e < 32; e += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-                o.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-                o.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-                o.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
-                *reinterpret_cast<uint4*>(dst + e) = o;
-              }
-            }
-          }
-          tcgen05_fence_before();
-        }
-      }  // j
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (is_control) {
-    tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-int launch_attn_bwd_tail(const void* qkv, long long ld, const uint8_t* mask, const void* d_o,
-                         long long lddo, const float* lse, const float* delta, void* dqkv,
-                         long long ldg, float* ws, int B, int H, int n, float scale,
-                         cudaStream_t stream);
 
 }  // namespace xclip
 
@@ -975,15 +504,7 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
   p.scale_log2 = scale * 1.4426950408889634f;
   p.mask = key_mask; p.lse = lse; p.delta = delta;
   p.dqkv = reinterpret_cast<bf16*>(dqkv); p.ld = ld_dqkv; p.dq_ws = dq_workspace;
-  p.tail = (attn_tail_enabled() && n > kBT && n % kBT == 1) ? 1 : 0;
-  p.nt = p.tail ? n - 1 : n;
-  p.qkv = reinterpret_cast<const bf16*>(qkv); p.ld_qkv = ld_qkv;
-  p.d_o = reinterpret_cast<const bf16*>(d_o); p.lddo = lddo;
-  if (p.tail) {
-    rc = launch_attn_bwd_tail(qkv, ld_qkv, key_mask, d_o, lddo, lse, delta, dqkv, ld_dqkv,
-                              dq_workspace, B, n, heads, scale, s);
-    if (rc) return rc;
-  }
+  p.nt = n;
 
   CUtensorMap tq, tdo;
   rc = encode_3d_bf16(&tq, qkv, (uint64_t)(3 * heads * kBDh), (uint64_t)n, (uint64_t)B,
@@ -993,27 +514,11 @@ extern "C" int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* ke
                       (uint64_t)lddo, (uint64_t)n * lddo, kBDh, kBT);
   if (rc) return rc;
 
-  const int smem = 12 * kBBox + 128 + 2 * 128 * 4 + 2 * 384 * 4 + 3 * 384 * 4 + 3 * 64 * 4;
-  static bool configured = false;
-  if (!configured) {
-    XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    smem));
-    configured = true;
-  }
+  const int smem = 12 * kBBox + 128 + 2 * 128 * 4 + 2 * 384 * 4;
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_kernel), smem);
+  if (rc) return rc;
   long long grid = num_sms();
   if (grid > (long long)B * heads) grid = (long long)B * heads;
-  static const bool use16 = [] { const char* e = getenv("XCLIP_ATTN_BWD16"); return e && e[0] == '1'; }();
-  if (use16) {
-    static bool configured16 = false;
-    if (!configured16) {
-      XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      smem));
-      configured16 = true;
-    }
-    attn_bwd16_kernel<<<(int)grid, kBwd16Threads, smem, s>>>(tq, tdo, p);
-    XCLIP_LAUNCH_CHECK("attn_bwd16_kernel");
-    return XCLIP_OK;
-  }
   attn_bwd_kernel<<<(int)grid, kBwdThreads, smem, s>>>(tq, tdo, p);
   XCLIP_LAUNCH_CHECK("attn_bwd_kernel");
   return XCLIP_OK;

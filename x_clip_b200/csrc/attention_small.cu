@@ -350,11 +350,8 @@ static int launch_fwd_small(const void* qkv, int64_t ld_qkv, const AttnSmallFwdP
                           (uint64_t)ld_qkv, (uint64_t)p.n * ld_qkv, kSDh, ROWS);
   if (rc) return rc;
   auto kern = attn_fwd_small_kernel<ROWS, kCausal>;
-  static bool configured = false;
-  if (!configured) {
-    XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), kSmem);
+  if (rc) return rc;
   long long grid = (long long)num_sms() * kPerSm;
   if (grid > (long long)p.B * p.H) grid = (long long)p.B * p.H;
   kern<<<(int)grid, kThreads, kSmem, stream>>>(tm, p);
@@ -675,15 +672,10 @@ int attn_bwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, con
                       (uint64_t)n * lddo, kSDh, (uint32_t)p.nkp);
   if (rc) return rc;
   const int smem = sbwd_smem_bytes(p.nkp);
-  static bool configured = false;
-  if (!configured) {
-    const int max_smem = sbwd_smem_bytes(128);
-    XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel<false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    XCLIP_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel<true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured = true;
-  }
+  rc = ensure_dynamic_smem(causal ? reinterpret_cast<const void*>(attn_bwd_small_kernel<true>)
+                                  : reinterpret_cast<const void*>(attn_bwd_small_kernel<false>),
+                           sbwd_smem_bytes(128));
+  if (rc) return rc;
   int per_sm = (227 * 1024) / (smem + 1024);
   if (per_sm > 2) per_sm = 2;      // 256 TMEM columns per CTA
   if (per_sm < 1) per_sm = 1;

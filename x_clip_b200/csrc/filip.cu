@@ -150,10 +150,9 @@ extern "C" int xclip_filip_segmax(const void* a, const void* b, int R, int C, in
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   using S = GemmSmem<256>;
   auto kern = gemm_bf16_kernel<256, kMajorK, kMajorK, EPI_SEGMAX>;
-  static bool configured = false;
-  if (!configured) {
-    XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), S::kTotal);
+    if (rc_attr) return rc_attr;
   }
   kern<<<grid, kGemmThreads, S::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmA, p);
   XCLIP_LAUNCH_CHECK("gemm_bf16_kernel<segmax>");

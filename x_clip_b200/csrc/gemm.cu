@@ -9,10 +9,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        const GemmParams& p, int grid, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MAJOR, B_MAJOR>;
-  static bool configured = false;
-  if (!configured) {
-    XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), S::kTotal);
+    if (rc_attr) return rc_attr;
   }
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmC, p);
   XCLIP_LAUNCH_CHECK("gemm_bf16_kernel");

@@ -4,7 +4,9 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace xclip {
 
@@ -68,12 +70,21 @@ static int do_init() {
 
 int num_sms() { return g_sms; }
 
-bool attn_tail_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("XCLIP_ATTN_TAIL");
-    return e && e[0] == '1';   // opt-in until the path has been validated on hardware
-  }();
-  return on;
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(XCLIP_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = done[std::make_pair(dev, kernel)];
+  if (cur >= bytes) return XCLIP_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess)
+    return fail(XCLIP_ERR_CUDA, "cudaFuncSetAttribute(%d B dynamic smem) failed: %s", bytes,
+                cudaGetErrorString(e));
+  cur = bytes;
+  return XCLIP_OK;
 }
 
 int encode_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,

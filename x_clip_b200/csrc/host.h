@@ -18,9 +18,9 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 
-// XCLIP_ATTN_TAIL=1 enables the CUDA-core tail-token path of the attention kernels (n = 128k+1);
-// off by default: it has not been validated on a B200 yet
-bool attn_tail_enabled();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): the attribute is
+// per device, so a process driving several GPUs must set it on each of them
+int ensure_dynamic_smem(const void* kernel, int bytes);
 
 // counts kernel launches made by this library (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);

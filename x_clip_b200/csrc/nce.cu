@@ -47,10 +47,9 @@ static int launch_nce(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
                       int grid, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   auto kern = gemm_bf16_kernel<BLOCK_N, kMajorK, kMajorK, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    XCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), S::kTotal);
+    if (rc_attr) return rc_attr;
   }
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmA, p);
   XCLIP_LAUNCH_CHECK("gemm_bf16_kernel<nce>");

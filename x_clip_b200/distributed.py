@@ -22,6 +22,24 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def assert_equal_local_batch(b: int, device: torch.device) -> None:
+    """Every rank must contribute the same number of rows (the reference pads to the largest
+    batch instead, distributed.py:18-33; here unequal batches are an error, not a hang): one
+    tiny MAX all-reduce of (b, -b); the comparison stays on the device (`_assert_async`), so no
+    host synchronisation is added to the step."""
+    if world()[1] == 1:
+        return
+    t = torch.tensor([b, -b], device=device, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = (t[0] + t[1]) == 0                       # max(b) == min(b)
+    if device.type == "cuda":
+        torch._assert_async(ok, "x_clip_b200: ranks hold different local batch sizes (unsupported; "
+                                "use drop_last or pad the last batch)")
+    elif not bool(ok):
+        raise RuntimeError("x_clip_b200: ranks hold different local batch sizes (unsupported; "
+                           "use drop_last or pad the last batch)")
+
+
 def gather_rows(shards: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """Each shard is this rank's [b, D] block of one latent set.  Returns, per set, the
     [W*b, D] matrix whose rows r*b..(r+1)*b-1 are rank r's - one collective for all sets."""
@@ -30,7 +48,8 @@ def gather_rows(shards: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         return [s.contiguous() for s in shards]
     b, D = shards[0].shape
     for s in shards:
-        assert tuple(s.shape) == (b, D), "all ranks must hold equal local batches of every latent set"
+        assert tuple(s.shape) == (b, D), "every latent set must have the same local shape"
+    assert_equal_local_batch(b, shards[0].device)
     stacked = torch.stack(list(shards)).contiguous()                       # [k, b, D]
     out = torch.empty(w * stacked.numel(), device=stacked.device, dtype=stacked.dtype)
     dist.all_gather_into_tensor(out, stacked.view(-1))                     # flat: backend agnostic
@@ -69,6 +88,32 @@ def reduce_scatter_rows(t: torch.Tensor) -> torch.Tensor:
     out = torch.empty((rows,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
     dist.reduce_scatter_tensor(out, t)
     return out
+
+
+_active_syncs: List["GradSync"] = []
+
+
+class defer_grad_sync:
+    """`with defer_grad_sync(flag):` - when flag is true, backward passes inside accumulate
+    parameter gradients without triggering any live GradSync (used by the micro-batched step,
+    engine.ChunkedClipLossFn, whose backward runs one autograd pass per chunk)."""
+
+    def __init__(self, flag: bool = True):
+        self.flag = flag
+        self.saved = []
+
+    def __enter__(self):
+        if self.flag:
+            self.saved = [(s, s.enabled) for s in _active_syncs]
+            for s in _active_syncs:
+                s.enabled = False
+        return self
+
+    def __exit__(self, *exc):
+        for s, e in self.saved:
+            s.enabled = e
+        self.saved = []
+        return False
 
 
 class GradSync:
@@ -118,6 +163,7 @@ class GradSync:
             self._add_bucket(cur)
         for p in params:
             self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        _active_syncs.append(self)
 
     def _add_bucket(self, params):
         b = {"params": list(params), "arrived": 0, "work": None, "flat": None, "members": None}
@@ -142,6 +188,11 @@ class GradSync:
         if not self.enabled:
             return
         b = self._bucket_of[p]
+        if b["work"] is not None or b["members"] is not None:
+            raise RuntimeError(
+                "GradSync: a parameter received a second gradient after its bucket was reduced - "
+                "several backward passes per step must run under `sync.no_sync()` / "
+                "`defer_grad_sync()` except the last one")
         b["arrived"] += 1
         if b["arrived"] == len(b["params"]):
             self._launch(b)
@@ -182,3 +233,5 @@ class GradSync:
         for h in self._handles:
             h.remove()
         self._handles = []
+        if self in _active_syncs:
+            _active_syncs.remove(self)

@@ -14,8 +14,6 @@ from __future__ import annotations
 
 from typing import List, Optional
 
-import weakref
-
 import torch
 
 from . import kernels as K
@@ -25,28 +23,46 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 LN_EPS = 1e-5   # the reference's fp32 branch (x_clip.py:118); parameters/outputs are fp32-facing
 
-_bf16_cache = {}
+_scope_cache = None     # dict while a weight_scope() is active, else None
 
 
 def weight_bf16(p: torch.Tensor) -> torch.Tensor:
-    """bf16 copy of an fp32 parameter, cached until the parameter is modified in place.
+    """bf16 copy of an fp32 parameter (the MMA operand).
 
-    The entry is validated by a weak reference to the parameter object itself (ids and data
-    pointers are recycled once a model is freed), its version counter and its storage address."""
-    key = id(p)
-    hit = _bf16_cache.get(key)
-    if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2] == p.data_ptr():
-        return hit[3]
+    Cast afresh on every call: a cache validated by `p._version` goes stale under `p.data.add_()`
+    style updates (Lion/LARS-type optimizers, EMA swaps, clamping), which do not bump the version
+    counter - the kernels would silently keep training on old weights.  Forward schedules keep
+    the casts they used in `ctx` for their backward (autograd semantics: backward sees the weights
+    of its forward).  Only inside an explicit `weight_scope()` - one micro-batched forward or
+    backward sweep, during which no optimizer can run - are casts shared between calls."""
+    if _scope_cache is not None:
+        hit = _scope_cache.get(id(p))
+        if hit is not None and hit[0] is p:
+            return hit[1]
     w = K.cast_bf16(p.detach())
-    if len(_bf16_cache) > 4096:          # drop entries of models that no longer exist
-        for k in [k for k, v in _bf16_cache.items() if v[0]() is None]:
-            del _bf16_cache[k]
-    _bf16_cache[key] = (weakref.ref(p), p._version, p.data_ptr(), w)
+    if _scope_cache is not None:
+        _scope_cache[id(p)] = (p, w)     # holds p: ids cannot be recycled inside the scope
     return w
 
 
+class weight_scope:
+    """Share bf16 weight casts between the encoder calls of ONE sweep over micro-batches."""
+
+    def __enter__(self):
+        global _scope_cache
+        self.prev = _scope_cache
+        if _scope_cache is None:
+            _scope_cache = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _scope_cache
+        _scope_cache = self.prev
+        return False
+
+
 def clear_weight_cache() -> None:
-    _bf16_cache.clear()
+    """Kept for API compatibility: there is no persistent cache any more."""
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -110,17 +126,20 @@ class TransformerFn(torch.autograd.Function):
         mask_c = None if mask is None else mask.contiguous()
 
         saved = []
+        # bf16 MMA operands of this call's weights; backward reuses exactly these (ctx.wb)
+        wb = [tuple(weight_bf16(w) for w in (l[1], l[2], l[5], l[7])) for l in layers]
         # norm_in fused with the first pre-norm
         xcur, st_in, xn, st1 = K.layernorm_fwd(x_in, g_in, g2=layers[0][0], eps=LN_EPS)
         for L, (g1, wqkv, wo, go, g2, w1, g4, w2) in enumerate(layers):
-            qkv = K.gemm(xn, weight_bf16(wqkv))
+            bqkv, bo, b1, b2 = wb[L]
+            qkv = K.gemm(xn, bqkv)
             o, lse = K.attn_fwd(qkv, mask_c, B, n, heads, scale)
-            y = K.gemm(o, weight_bf16(wo))
+            y = K.gemm(o, bo)
             # x1 = LN(y)*go + x ; xn2 = LN(x1)*g2   (attention tail + feed-forward pre-norm)
             x1, st_y, xn2, st_x1 = K.layernorm_fwd(y, go, res=xcur, g2=g2, eps=LN_EPS)
-            u = K.gemm(xn2, weight_bf16(w1))
+            u = K.gemm(xn2, b1)
             h, st_v = K.geglu_ln_fwd(u, g4, eps=LN_EPS)
-            x2 = K.gemm(h, weight_bf16(w2), residual=x1)
+            x2 = K.gemm(h, b2, residual=x1)
             saved.append((xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h))
             xcur = x2
             if L + 1 < depth:
@@ -132,6 +151,7 @@ class TransformerFn(torch.autograd.Function):
         ctx.mask = mask_c
         ctx.dims = (B, n, d, heads, depth, scale)
         ctx.weights = weights
+        ctx.wb = wb
         return out.view(B, n, d)
 
     @staticmethod
@@ -157,15 +177,16 @@ class TransformerFn(torch.autograd.Function):
             g1, wqkv, wo, go, g2, w1, g4, w2 = layers[L]
             xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h = ctx.saved[L]
             ctx.saved[L] = None
+            bqkv, bo, b1, b2 = ctx.wb[L]
             base = 2 + 8 * L
             # feed-forward: x2 = h @ w2^T + x1
-            dh = K.gemm(dx, weight_bf16(w2), b_major=1)
+            dh = K.gemm(dx, b2, b_major=1)
             grads[base + 7] = wg.wgrad(dx, h)
             dg4 = torch.zeros(g4.shape[0], device=dev, dtype=F32)
             du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
             grads[base + 6] = dg4
             del dh
-            dxn2 = K.gemm(du, weight_bf16(w1), b_major=1)
+            dxn2 = K.gemm(du, b1, b_major=1)
             grads[base + 5] = wg.wgrad(du, xn2)
             del du
             dg2 = torch.zeros(d, device=dev, dtype=F32)
@@ -175,10 +196,10 @@ class TransformerFn(torch.autograd.Function):
             dgo = torch.zeros(d, device=dev, dtype=F32)
             dy = K.layernorm_bwd(dx1, y, st_y, go, dg=dgo)
             grads[base + 3] = dgo
-            d_o = K.gemm(dy, weight_bf16(wo), b_major=1)
+            d_o = K.gemm(dy, bo, b_major=1)
             grads[base + 2] = wg.wgrad(dy, o)
             dqkv = K.attn_bwd(qkv, ctx.mask, o, d_o, lse, B, n, heads, scale)
-            dxn = K.gemm(dqkv, weight_bf16(wqkv), b_major=1)
+            dxn = K.gemm(dqkv, bqkv, b_major=1)
             grads[base + 1] = wg.wgrad(dqkv, xn)
             dg1 = torch.zeros(d, device=dev, dtype=F32)
             dx = K.layernorm_bwd(dxn, xcur, st1, g1, add=dx1, dg=dg1)
@@ -187,7 +208,7 @@ class TransformerFn(torch.autograd.Function):
         dx_in = K.layernorm_bwd(dx, x_in, st_in, g_in, dg=dg_in)
         grads[0] = dg_in
         wg.join()
-        ctx.saved = None
+        ctx.saved = ctx.wb = None
         return (dx_in.view(B, n, d), None, None, None, *grads)
 
 
@@ -221,20 +242,21 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, table):
         x = x.contiguous()
         tbl16 = None if table is None else K.cast_bf16(table.detach())
-        y = K.gemm(x, weight_bf16(weight), bias=None if bias is None else bias.detach(),
+        wb = weight_bf16(weight)
+        y = K.gemm(x, wb, bias=None if bias is None else bias.detach(),
                    residual=tbl16, res_row_mod=0 if table is None else table.shape[0])
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, wb)
         ctx.has_bias = bias is not None
         ctx.period = None if table is None else table.shape[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, wb = ctx.saved_tensors
         dy = dy.contiguous()
         if dy.dtype != BF16:
             dy = dy.to(BF16)
-        dx = K.gemm(dy, weight_bf16(weight), b_major=1) if ctx.needs_input_grad[0] else None
+        dx = K.gemm(dy, wb, b_major=1) if ctx.needs_input_grad[0] else None
         dw = _wgrad(dy, x)
         db = dy.float().sum(dim=0) if ctx.has_bias else None
         dt = None
@@ -250,17 +272,18 @@ class ProjectL2NormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, e, weight):
         e = e.contiguous()
-        p = K.gemm(e, weight_bf16(weight), out_dtype=F32)
+        wb = weight_bf16(weight)
+        p = K.gemm(e, wb, out_dtype=F32)
         z, zrow, zcol, inv = K.l2norm_fwd(p)
-        ctx.save_for_backward(e, weight, z, inv)
+        ctx.save_for_backward(e, wb, z, inv)
         ctx.mark_non_differentiable(zrow, zcol)
         return z, zrow, zcol
 
     @staticmethod
     def backward(ctx, dz, _a, _b):
-        e, weight, z, inv = ctx.saved_tensors
+        e, wb, z, inv = ctx.saved_tensors
         dp = K.l2norm_bwd(dz.contiguous().float(), z, inv)
-        de = K.gemm(dp, weight_bf16(weight), b_major=1) if ctx.needs_input_grad[0] else None
+        de = K.gemm(dp, wb, b_major=1) if ctx.needs_input_grad[0] else None
         dw = _wgrad(dp, e)
         return de, dw
 
@@ -364,7 +387,7 @@ class ChunkedClipLossFn(torch.autograd.Function):
         B = text.shape[0]
         bounds = [(s, min(s + chunk, B)) for s in range(0, B, chunk)]
         rng_states, zs, opss = [], [], []
-        with torch.no_grad():
+        with torch.no_grad(), weight_scope():
             for s, e in bounds:
                 rng_states.append(torch.cuda.get_rng_state(text.device))
                 z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
@@ -395,11 +418,16 @@ class ChunkedClipLossFn(torch.autograd.Function):
         dz = [l.grad for l in leaves]
         dev = text.device
         keep_state = torch.cuda.get_rng_state(dev)
-        for (s, e), st in zip(ctx.bounds, ctx.rng_states):
-            torch.cuda.set_rng_state(st, dev)
-            with torch.enable_grad():
-                z, _ = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
-                torch.autograd.backward(list(z), [d[s:e] for d in dz])   # accumulates into .grad
+        last = len(ctx.bounds) - 1
+        with weight_scope():
+            for k, ((s, e), st) in enumerate(zip(ctx.bounds, ctx.rng_states)):
+                torch.cuda.set_rng_state(st, dev)
+                # parameter gradients accumulate over the chunks; gradient-sync hooks (GradSync)
+                # must see a parameter ONCE per step, with its complete gradient: every chunk but
+                # the last runs with the hooks deferred (the DDP no_sync convention)
+                with torch.enable_grad(), D_.defer_grad_sync(k != last):
+                    z, _ = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                    torch.autograd.backward(list(z), [d[s:e] for d in dz])   # accumulates into .grad
         torch.cuda.set_rng_state(keep_state, dev)
         ctx.graph = ctx.inputs = None
         return None, None, None, None, None, temp_leaf.grad

@@ -16,8 +16,9 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: torch.Tensor) -> int:
+    """Current torch stream of the device the operands live on."""
+    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 class Profiler:
@@ -50,7 +51,17 @@ class Profiler:
 PROF = Profiler()
 
 
-def _call(family: str, flops: float, nbytes: float, name: str, *args) -> None:
+def _call(dev_of: torch.Tensor, family: str, flops: float, nbytes: float, name: str, *args) -> None:
+    """Launch on the device of `dev_of` (made current for the call: the library launches on
+    cudaGetDevice() and keeps per-device kernel attributes) and on its current torch stream."""
+    if dev_of.device.index != torch.cuda.current_device():
+        with torch.cuda.device(dev_of.device):
+            _call_on_current(family, flops, nbytes, name, *args, _stream(dev_of))
+        return
+    _call_on_current(family, flops, nbytes, name, *args, _stream(dev_of))
+
+
+def _call_on_current(family: str, flops: float, nbytes: float, name: str, *args) -> None:
     if not PROF.enabled:
         _lib.call(name, *args)
         return
@@ -114,10 +125,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
         ldr = residual.stride(0)
     fam = "gemm_wgrad" if (a_major == 1 and b_major == 1) else ("gemm_dgrad" if b_major == 1 else "gemm_fwd")
     nbytes = 2.0 * (M * K + N * K) + M * N * out.element_size() + (M * N * 2 if residual is not None else 0)
-    _call(fam, 2.0 * M * N * K, nbytes, "xclip_gemm_bf16", a.data_ptr(), a.stride(0), a_major, b.data_ptr(), b.stride(0),
+    _call(a, fam, 2.0 * M * N * K, nbytes, "xclip_gemm_bf16", a.data_ptr(), a.stride(0), a_major, b.data_ptr(), b.stride(0),
               b_major, out.data_ptr(), out.stride(0), 1 if out.dtype == F32 else 0, M, N, K,
               float(alpha), _ptr(bias), _ptr(residual), ldr, int(res_row_mod),
-              1 if accumulate else 0, _stream())
+              1 if accumulate else 0)
     return out
 
 
@@ -127,8 +138,8 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     src = src.contiguous()
     dst = torch.empty(src.shape, device=src.device, dtype=BF16)
     if src.numel():
-        _call("cast", 0.0, 6.0 * src.numel(), "xclip_cast_f32_bf16", src.data_ptr(), dst.data_ptr(),
-              src.numel(), _stream())
+        _call(src, "cast", 0.0, 6.0 * src.numel(), "xclip_cast_f32_bf16", src.data_ptr(), dst.data_ptr(),
+              src.numel())
     return dst
 
 
@@ -146,10 +157,10 @@ def layernorm_fwd(x, g, *, res=None, g2=None, eps=1e-5, want_stats=True):
     if res is not None:
         _need(res, BF16, "res"); _rows2d(res, "res")
     passes = 2 + (1 if res is not None else 0) + (1 if g2 is not None else 0)
-    _call("layernorm_fwd", 0.0, 2.0 * rows * d * passes, "xclip_layernorm_fwd", x.data_ptr(), x.stride(0), g.data_ptr(), _ptr(res),
+    _call(x, "layernorm_fwd", 0.0, 2.0 * rows * d * passes, "xclip_layernorm_fwd", x.data_ptr(), x.stride(0), g.data_ptr(), _ptr(res),
               res.stride(0) if res is not None else 0, out.data_ptr(), out.stride(0), _ptr(stats),
               _ptr(g2), _ptr(out2), out2.stride(0) if out2 is not None else 0, _ptr(stats2),
-              rows, d, float(eps), _stream())
+              rows, d, float(eps))
     return out, stats, out2, stats2
 
 
@@ -160,10 +171,10 @@ def layernorm_bwd(dy, x, stats, g, *, add=None, dg=None):
     dx = torch.empty((rows, d), device=x.device, dtype=BF16)
     if add is not None:
         _need(add, BF16, "add"); _rows2d(add, "add")
-    _call("layernorm_bwd", 0.0, 2.0 * rows * d * (3 + (1 if add is not None else 0)),
+    _call(dy, "layernorm_bwd", 0.0, 2.0 * rows * d * (3 + (1 if add is not None else 0)),
           "xclip_layernorm_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
               stats.data_ptr(), g.data_ptr(), _ptr(add), add.stride(0) if add is not None else 0,
-              dx.data_ptr(), dx.stride(0), _ptr(dg), rows, d, _stream())
+              dx.data_ptr(), dx.stride(0), _ptr(dg), rows, d)
     return dx
 
 
@@ -173,8 +184,8 @@ def geglu_ln_fwd(u, g, *, eps=1e-5):
     dh = two_dh // 2
     h = torch.empty((rows, dh), device=u.device, dtype=BF16)
     stats = torch.empty((rows, 2), device=u.device, dtype=F32)
-    _call("geglu_ln_fwd", 0.0, 2.0 * rows * dh * 3, "xclip_geglu_ln_fwd", u.data_ptr(), u.stride(0), g.data_ptr(), h.data_ptr(),
-              h.stride(0), stats.data_ptr(), rows, dh, float(eps), _stream())
+    _call(u, "geglu_ln_fwd", 0.0, 2.0 * rows * dh * 3, "xclip_geglu_ln_fwd", u.data_ptr(), u.stride(0), g.data_ptr(), h.data_ptr(),
+              h.stride(0), stats.data_ptr(), rows, dh, float(eps))
     return h, stats
 
 
@@ -182,9 +193,9 @@ def geglu_ln_bwd(dh_grad, u, stats, g, *, dg=None):
     _need(dh_grad, BF16, "dh"); _rows2d(dh_grad, "dh"); _need(u, BF16, "u")
     rows, two_dh = u.shape
     du = torch.empty((rows, two_dh), device=u.device, dtype=BF16)
-    _call("geglu_ln_bwd", 0.0, 2.0 * rows * (two_dh // 2) * 5, "xclip_geglu_ln_bwd", dh_grad.data_ptr(), dh_grad.stride(0), u.data_ptr(),
+    _call(dh_grad, "geglu_ln_bwd", 0.0, 2.0 * rows * (two_dh // 2) * 5, "xclip_geglu_ln_bwd", dh_grad.data_ptr(), dh_grad.stride(0), u.data_ptr(),
               u.stride(0), stats.data_ptr(), g.data_ptr(), du.data_ptr(), du.stride(0), _ptr(dg),
-              rows, two_dh // 2, _stream())
+              rows, two_dh // 2)
     return du
 
 
@@ -195,8 +206,8 @@ def l2norm_fwd(p):
     zrow = torch.empty((rows, 3 * d), device=p.device, dtype=BF16)
     zcol = torch.empty((rows, 3 * d), device=p.device, dtype=BF16)
     inv = torch.empty((rows,), device=p.device, dtype=F32)
-    _call("l2norm", 0.0, rows * d * (4 + 4 + 12), "xclip_l2norm_fwd", p.data_ptr(), p.stride(0), z.data_ptr(), zrow.data_ptr(),
-              zcol.data_ptr(), inv.data_ptr(), rows, d, _stream())
+    _call(p, "l2norm", 0.0, rows * d * (4 + 4 + 12), "xclip_l2norm_fwd", p.data_ptr(), p.stride(0), z.data_ptr(), zrow.data_ptr(),
+              zcol.data_ptr(), inv.data_ptr(), rows, d)
     return z, zrow, zcol, inv
 
 
@@ -205,8 +216,8 @@ def l2norm_bwd(dz, z, inv):
     dz = dz.contiguous()
     rows, d = z.shape
     dp = torch.empty((rows, d), device=z.device, dtype=BF16)
-    _call("l2norm", 0.0, rows * d * (4 + 4 + 2), "xclip_l2norm_bwd", dz.data_ptr(), z.data_ptr(), inv.data_ptr(), dp.data_ptr(),
-              rows, d, _stream())
+    _call(dz, "l2norm", 0.0, rows * d * (4 + 4 + 2), "xclip_l2norm_bwd", dz.data_ptr(), z.data_ptr(), inv.data_ptr(), dp.data_ptr(),
+              rows, d)
     return dp
 
 
@@ -218,8 +229,8 @@ def attn_fwd(qkv, key_mask, B, n, heads, scale, causal=False):
     if key_mask is not None:
         if key_mask.dtype != torch.bool or tuple(key_mask.shape) != (B, n) or not key_mask.is_contiguous():
             raise _lib.XClipB200Error("attn_fwd: key_mask must be a contiguous bool [B, n]")
-    _call("attn_fwd", 4.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 4, "xclip_attn_fwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
-              o.stride(0), lse.data_ptr(), B, n, heads, float(scale), 1 if causal else 0, _stream())
+    _call(qkv, "attn_fwd", 4.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 4, "xclip_attn_fwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
+              o.stride(0), lse.data_ptr(), B, n, heads, float(scale), 1 if causal else 0)
     return o, lse
 
 
@@ -228,10 +239,10 @@ def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale, causal=False):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, heads, n), device=qkv.device, dtype=F32)
     ws = torch.empty((B * n, heads * 64), device=qkv.device, dtype=F32) if n > 128 else None
-    _call("attn_bwd", 10.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 8, "xclip_attn_bwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
+    _call(qkv, "attn_bwd", 10.0 * B * heads * n * n * 64, 2.0 * B * n * heads * 64 * 8, "xclip_attn_bwd", qkv.data_ptr(), qkv.stride(0), _ptr(key_mask), o.data_ptr(),
               o.stride(0), d_o.data_ptr(), d_o.stride(0), lse.data_ptr(), delta.data_ptr(),
               dqkv.data_ptr(), dqkv.stride(0), _ptr(ws), B, n, heads, float(scale),
-              1 if causal else 0, _stream())
+              1 if causal else 0)
     return dqkv
 
 
@@ -245,9 +256,9 @@ def nce_fwd(a, b, temp_exp, diag_offset, dcl, loss_accum=None, loss_scale=0.0):
     part = torch.empty((nblk, R), device=a.device, dtype=F32)
     pos = torch.empty((R,), device=a.device, dtype=F32)
     lse = torch.empty((R,), device=a.device, dtype=F32)
-    _call("nce_fwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R, "xclip_nce_fwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
+    _call(a, "nce_fwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R, "xclip_nce_fwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
               int(diag_offset), 1 if dcl else 0, part.data_ptr(), pos.data_ptr(), lse.data_ptr(),
-              _ptr(loss_accum), float(loss_scale), _stream())
+              _ptr(loss_accum), float(loss_scale))
     return lse, pos
 
 
@@ -259,10 +270,9 @@ def nce_bwd(a, b, temp_exp, diag_offset, dcl, lse_row, lse_col, w_row, w_col, w_
     C = b.shape[0]
     ldg = (C + 7) // 8 * 8
     g = torch.empty((R, ldg), device=a.device, dtype=BF16)
-    _call("nce_bwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 2.0 * R * C, "xclip_nce_bwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
+    _call(a, "nce_bwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 2.0 * R * C, "xclip_nce_bwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
               int(diag_offset), 1 if dcl else 0, _ptr(lse_row), _ptr(lse_col), float(w_row),
-              float(w_col), float(w_diag), gscale.data_ptr(), g.data_ptr(), ldg, _ptr(dtemp),
-              _stream())
+              float(w_col), float(w_diag), gscale.data_ptr(), g.data_ptr(), ldg, _ptr(dtemp))
     return g
 
 
@@ -274,43 +284,42 @@ def filip_segmax(a, b, temp_exp, seg_len, col_mul, col_add):
     nseg = C // seg_len
     seg_max = torch.empty((R, nseg), device=a.device, dtype=F32)
     seg_arg = torch.empty((R, nseg), device=a.device, dtype=torch.int32)
-    _call("filip_segmax", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R * nseg, "xclip_filip_segmax",
+    _call(a, "filip_segmax", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R * nseg, "xclip_filip_segmax",
           a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(), int(seg_len), _ptr(col_mul),
-          _ptr(col_add), seg_max.data_ptr(), seg_arg.data_ptr(), _stream())
+          _ptr(col_add), seg_max.data_ptr(), seg_arg.data_ptr())
     return seg_max, seg_arg
 
 
 def filip_reduce(seg_max, weights, samples, length, nseg, transpose):
     out = torch.empty((nseg, samples) if transpose else (samples, nseg), device=seg_max.device, dtype=F32)
-    _call("filip_small", 0.0, 4.0 * seg_max.numel(), "xclip_filip_reduce", seg_max.data_ptr(),
-          weights.data_ptr(), samples, length, nseg, out.data_ptr(), 1 if transpose else 0, _stream())
+    _call(seg_max, "filip_small", 0.0, 4.0 * seg_max.numel(), "xclip_filip_reduce", seg_max.data_ptr(),
+          weights.data_ptr(), samples, length, nseg, out.data_ptr(), 1 if transpose else 0)
     return out
 
 
 def filip_nce_fwd(s, diag_off, dcl, loss_accum, loss_scale):
     R, C = s.shape
     lse = torch.empty((R,), device=s.device, dtype=F32)
-    _call("filip_small", 0.0, 4.0 * s.numel(), "xclip_filip_nce_fwd", s.data_ptr(), R, C,
-          int(diag_off), 1 if dcl else 0, lse.data_ptr(), _ptr(loss_accum), float(loss_scale),
-          _stream())
+    _call(s, "filip_small", 0.0, 4.0 * s.numel(), "xclip_filip_nce_fwd", s.data_ptr(), R, C,
+          int(diag_off), 1 if dcl else 0, lse.data_ptr(), _ptr(loss_accum), float(loss_scale))
     return lse
 
 
 def filip_nce_bwd(s, lse, diag_off, dcl, gscale):
     R, C = s.shape
     g = torch.empty_like(s)
-    _call("filip_small", 0.0, 8.0 * s.numel(), "xclip_filip_nce_bwd", s.data_ptr(), lse.data_ptr(), R,
-          C, int(diag_off), 1 if dcl else 0, gscale.data_ptr(), g.data_ptr(), _stream())
+    _call(s, "filip_small", 0.0, 8.0 * s.numel(), "xclip_filip_nce_bwd", s.data_ptr(), lse.data_ptr(), R,
+          C, int(diag_off), 1 if dcl else 0, gscale.data_ptr(), g.data_ptr())
     return g
 
 
 def filip_expand(seg_arg, seg_max, wmat, rowscale, temp_exp, row0, rows, rows_per_sample, seg_len,
                  nseg, dtemp):
     g = torch.empty((rows, nseg * seg_len), device=seg_arg.device, dtype=BF16)
-    _call("filip_expand", 0.0, 2.0 * g.numel(), "xclip_filip_expand", seg_arg.data_ptr(),
+    _call(seg_arg, "filip_expand", 0.0, 2.0 * g.numel(), "xclip_filip_expand", seg_arg.data_ptr(),
           seg_max.data_ptr(), wmat.data_ptr(), rowscale.data_ptr(), temp_exp.data_ptr(), int(row0),
           int(rows), int(rows_per_sample), int(seg_len), int(nseg), g.data_ptr(), g.stride(0),
-          _ptr(dtemp), _stream())
+          _ptr(dtemp))
     return g
 
 
@@ -318,12 +327,17 @@ def text_embed_fwd(ids, tok, pos, cls):
     """ids int64 [B,n] -> bf16 [B, n+1, d] = [cls | tok[ids] + pos]."""
     if ids.dtype != torch.int64 or not ids.is_cuda:
         raise _lib.XClipB200Error("text_embed: ids must be a CUDA int64 tensor")
+    _need(tok, F32, "token table"); _need(pos, F32, "position table"); _need(cls, F32, "cls token")
+    if not (tok.is_contiguous() and pos.is_contiguous() and cls.is_contiguous()):
+        raise _lib.XClipB200Error("text_embed: embedding tables must be contiguous")
     ids = ids.contiguous()
     B, n = ids.shape
     vocab, d = tok.shape
+    if pos.shape[0] < n or pos.shape[1] != d or cls.numel() != d:
+        raise _lib.XClipB200Error("text_embed: table shapes do not match the ids")
     out = torch.empty((B, n + 1, d), device=ids.device, dtype=BF16)
-    _call("embed", 0.0, B * (n + 1) * d * 6.0, "xclip_text_embed_fwd", ids.data_ptr(), tok.data_ptr(),
-          pos.data_ptr(), cls.data_ptr(), out.data_ptr(), B, n, d, vocab, _stream())
+    _call(ids, "embed", 0.0, B * (n + 1) * d * 6.0, "xclip_text_embed_fwd", ids.data_ptr(), tok.data_ptr(),
+          pos.data_ptr(), cls.data_ptr(), out.data_ptr(), B, n, d, vocab)
     return out
 
 
@@ -332,9 +346,10 @@ def text_embed_bwd(ids, dx, vocab, pos_rows):
     B, n = ids.shape
     d = dx.shape[-1]
     dx = dx.contiguous()
+    _need(dx, BF16, "dx")
     dtok = torch.zeros((vocab, d), device=dx.device, dtype=F32)
     dpos = torch.zeros((pos_rows, d), device=dx.device, dtype=F32)
     dcls = torch.zeros((d,), device=dx.device, dtype=F32)
-    _call("embed", 0.0, B * (n + 1) * d * 8.0, "xclip_text_embed_bwd", ids.data_ptr(), dx.data_ptr(),
-          dtok.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, n, d, vocab, _stream())
+    _call(ids, "embed", 0.0, B * (n + 1) * d * 8.0, "xclip_text_embed_bwd", ids.data_ptr(), dx.data_ptr(),
+          dtok.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, n, d, vocab)
     return dtok, dpos, dcls
