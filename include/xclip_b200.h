@@ -125,7 +125,8 @@ int xclip_attn_bwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, con
  *   r + diag_offset.  dcl != 0 removes the positive from the denominator (:834-836).
  * fwd:  lse[r] = log sum_c exp(s[r,c]);  pos[r] = s[r, r+diag_offset];
  *       *loss_accum += loss_scale * sum_r (lse[r] - pos[r])     (loss_accum may be NULL)
- *       part_ws: f32 scratch [xclip_nce_num_col_blocks(C) * R].
+ *       part_ws: f32 scratch [2 * xclip_nce_num_col_blocks(C) * R] (per block: max, sum; the
+ *       log-sum-exp uses an online maximum, so any temperature works).
  *       (the reference's +1e-20 inside its logs, :51-52, is below fp32 resolution here)
  * bwd:  g[r,c] = *gscale * (w_row*exp(s - lse_row[r]) + w_col*exp(s - lse_col[c])
  *                           - w_diag*[c == r+diag])     (gscale: DEVICE scalar, upstream grad
@@ -172,7 +173,8 @@ int xclip_filip_expand(const int* seg_arg, const float* seg_max, const float* wm
 
 /* ---- text embedding (x_clip/x_clip.py:320-332) ---------------------------------------------
  * fwd: out bf16 [B, n+1, d]: out[b,0] = cls, out[b,1+t] = tok[ids[b,t]] + pos[t]  (fp32 tables,
- *      ids int64 [B,n], clamped to [0, vocab)).
+ *      ids int64 [B,n]; an id outside [0, vocab) traps the kernel - the launch
+ *      fails like nn.Embedding's device-side assert, nothing is clamped silently).
  * bwd: dx bf16 [B, n+1, d] -> dtok f32 [vocab,d] (+=, vector reductions), dpos f32 [>=n, d] (+=),
  *      dcls f32 [d] (+=).  All three gradients must be zero-initialised by the caller. */
 int xclip_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos, const float* cls,

@@ -33,6 +33,16 @@ README = dict(dim_text=512, dim_image=512, dim_latent=512, num_text_tokens=10000
               text_enc_depth=6, text_seq_len=256, text_heads=8, visual_enc_depth=6,
               visual_image_size=256, visual_patch_size=32, visual_heads=8)
 
+# ViT-B/16-SHAPED towers (cfg3 of BASELINE.json at depth 2): dim_image 768 / 12 heads / 224 px / patch 16
+# -> 196 patches (98 kept with the default patch dropout), text 77 tokens + CLS, CLIP-size latent
+VITB16_2L = dict(dim_text=512, dim_image=768, dim_latent=512, num_text_tokens=1000, text_enc_depth=2,
+                 text_seq_len=77, text_heads=8, visual_enc_depth=2, visual_heads=12,
+                 visual_image_size=224, visual_patch_size=16)
+# FILIP at the token counts of cfg4: 256 text tokens x 64 (32 with patch dropout) image tokens
+FILIP_T256 = dict(dim_text=256, dim_image=256, dim_latent=256, num_text_tokens=512, text_enc_depth=1,
+                  text_seq_len=256, text_heads=4, visual_enc_depth=1, visual_heads=4,
+                  visual_image_size=256, visual_patch_size=32, use_all_token_embeds=True)
+
 CASES = {
     # name: (cfg overrides, batch, pad_fraction, patch_dropout)
     "tiny_plain": (dict(TINY), 6, 0.2, 0.0),
@@ -45,6 +55,11 @@ CASES = {
                                   extra_latent_projection=True), 4, 0.25, 0.0),
     "tiny_patchdrop": (dict(TINY), 6, 0.2, 0.5),
     "readme_plain": (dict(README), 4, 0.0, 0.0),
+    "vitb16_shaped": (dict(VITB16_2L), 4, 0.1, 0.0),          # image attention n = 196, text n = 78
+    "vitb16_shaped_drop": (dict(VITB16_2L), 4, 0.1, 0.5),     # image attention n = 98 (cfg3 bench shape)
+    "filip_t256": (dict(FILIP_T256), 3, 0.3, 0.0),            # T = 256, I = 64
+    "filip_t256_drop": (dict(FILIP_T256), 3, 0.3, 0.5),       # T = 256, I = 32
+    "tiny_b64": (dict(TINY), 64, 0.2, 0.0),                   # batch large enough for the 1e-2 d temperature gate
 }
 WEIGHT_SEED = 1234
 INPUT_SEED = 4321

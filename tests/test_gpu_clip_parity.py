@@ -17,7 +17,10 @@ pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
 
 TINY_CASES = ["tiny_plain", "tiny_nomask", "tiny_dcl", "tiny_extra", "tiny_dcl_extra", "tiny_patchdrop",
-              "tiny_filip", "tiny_filip_dcl_extra"]
+              "tiny_filip", "tiny_filip_dcl_extra",
+              # BASELINE cfg3-shaped towers at depth 2 (d_image 768, 12 heads, n = 196 / 98 image tokens,
+              # 78 text tokens) and cfg4's FILIP token counts (T = 256, I = 64 / 32)
+              "vitb16_shaped", "vitb16_shaped_drop", "filip_t256", "filip_t256_drop"]
 
 
 def _run(case, dev):
@@ -83,6 +86,63 @@ def test_clip_matches_reference(cuda_device, case):
         if cos < 0.99 or nrel > 5e-2:
             bad.append((k, round(cos, 4), round(nrel, 4)))
     assert not bad, bad
+
+
+def test_dtemperature_at_batch_64_meets_the_survey_gate(cuda_device):
+    """SURVEY 8d gate: d loss / d temperature within 1e-2 RELATIVE, end to end.  At the 4-6 sample
+    cases above the gradient is a cancellation of O(1) terms (see the module docstring); at batch 64
+    it is not, and the plain relative gate holds."""
+    gold, loss, grads, lat, o_loss, p = _run("tiny_b64", cuda_device)
+    assert abs(loss - gold["loss"]) <= 1e-3 * abs(gold["loss"])
+    dt = grads["temperature"].item()
+    assert abs(dt - gold["dtemperature"]) <= 1e-2 * abs(gold["dtemperature"]), (dt, gold["dtemperature"])
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+    assert abs(gn - gold["grad_norm"]) <= 1e-2 * gold["grad_norm"], (gn, gold["grad_norm"])
+
+
+@pytest.mark.parametrize("case", ["tiny_plain", "tiny_dcl", "tiny_extra", "tiny_dcl_extra", "tiny_b64"])
+def test_dtemperature_of_the_loss_kernels_in_isolation(cuda_device, case):
+    """Feed the ORACLE the GPU's own latents: the similarity + InfoNCE/DCL forward/backward kernels
+    (EPI_NCE_FWD / EPI_NCE_BWD) are then compared without any encoder noise.  Loss rel <= 1e-5,
+    d temperature rel <= 1e-3 (+1e-6 abs), latent gradients rel <= 2e-3."""
+    from oracle import clip_oracle as O
+    import x_clip_b200
+    gold = json.loads((GOLD / f"{case}.json").read_text())
+    cfg = O.ClipConfig(**gold["cfg"])
+    state = O.protocol_state_dict(cfg, gold["weight_seed"])
+    text, image = O.protocol_inputs(cfg, gold["batch"], gold["input_seed"], gold["pad_fraction"])
+    clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0.).to(cuda_device)
+    clip.load_state_dict(state)
+    clip.train()
+    lat = clip(text.to(cuda_device), image.to(cuda_device), return_latents=True)
+    lat = [z.detach().requires_grad_(True) for z in lat]
+    if len(lat) == 2:
+        lat = lat + lat
+    ops = []
+    from x_clip_b200 import kernels as K
+    for z in (lat if cfg.extra_latent_projection else lat[:2]):
+        # the split-bf16 operands of exactly these fp32 latents (what ProjectL2NormFn hands the loss)
+        hi = z.detach().to(torch.bfloat16)
+        lo = (z.detach() - hi.float()).to(torch.bfloat16)
+        ops.append((torch.cat([hi, lo, hi], 1).contiguous(), torch.cat([hi, hi, lo], 1).contiguous()))
+    temp = clip.temperature.detach().clone().requires_grad_(True)
+    from x_clip_b200 import engine as E
+    loss = E.ContrastiveLossFn.apply(lat[0], lat[1], lat[2] if cfg.extra_latent_projection else None,
+                                     lat[3] if cfg.extra_latent_projection else None, temp, tuple(ops),
+                                     cfg.decoupled_contrastive_learning, False)
+    loss.backward()
+    zc = [z.detach().cpu().double().requires_grad_(True) for z in lat]
+    tc = temp.detach().cpu().double().requires_grad_(True)
+    ref = O.contrastive_loss(zc[0], zc[1], zc[2], zc[3], tc, cfg)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()), (loss.item(), ref.item())
+    assert abs(temp.grad.item() - tc.grad.item()) <= 1e-3 * abs(tc.grad.item()) + 1e-6, (temp.grad.item(), tc.grad.item())
+    n = 4 if cfg.extra_latent_projection else 2
+    for j in range(n):
+        g, r = lat[j].grad.cpu().double(), zc[j].grad
+        if n == 2 and j < 2:     # without extra projections zt_x/zi_x ARE zt/zi: their gradients add up
+            r = zc[j].grad + zc[j + 2].grad
+        assert (g - r).norm().item() <= 2e-3 * r.norm().item() + 1e-9, (j, (g - r).norm().item(), r.norm().item())
 
 
 def test_readme_config_matches_reference(cuda_device):

@@ -22,8 +22,13 @@ text_embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict
     const float* src = cls;
     const float* add = nullptr;
     if (j > 0) {
-      long long id = ids[b * n + (j - 1)];
-      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+      const long long id = ids[b * n + (j - 1)];
+      if (id < 0 || id >= vocab) {   // nn.Embedding raises a device-side assert here (x_clip.py:320)
+        if (lane == 0)
+          printf("xclip text_embed: token id %lld at [%lld,%d] outside the vocabulary [0,%d)\n", id,
+                 b, j - 1, vocab);
+        __trap();
+      }
       src = tok + id * d;
       add = pos + (long long)(j - 1) * d;
     }
@@ -54,8 +59,8 @@ text_embed_scatter_kernel(const long long* __restrict__ ids, const bf16* __restr
   for (long long r = warp; r < rows; r += nwarps) {
     const long long b = r / n;
     const int t = (int)(r % n);
-    long long id = ids[r];
-    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const long long id = ids[r];
+    if (id < 0 || id >= vocab) __trap();   // (the forward already reported it)
     const bf16* src = dx + (b * (n + 1) + 1 + t) * d;
     float* dst = dtok + id * d;
     for (int c = lane * 8; c < d; c += 256) {

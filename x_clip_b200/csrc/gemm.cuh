@@ -41,7 +41,7 @@ struct GemmParams {
   // ---- InfoNCE / DCL epilogues (EPI_NCE_FWD, EPI_NCE_BWD); logits s = alpha * acc, alpha = exp(temperature)
   int diag_offset;       // positive of local row r sits in column r + diag_offset
   int dcl;               // decoupled contrastive learning: drop the positive from the denominators
-  float* nce_part;       // FWD: [num_n_blocks, M] partial sums of exp(s - alpha)
+  float* nce_part;       // FWD: [num_n_blocks, M, 2] per block (max of x, sum of 2^(x - max)), x = s*log2(e)
   float* nce_pos;        // FWD: [M] positive logits
   const float* lse_row;  // BWD: [M]  log-denominator of each row (this direction)
   const float* lse_col;  // BWD: [N]  log-denominator of each column (other direction)
@@ -375,27 +375,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         }
       } else if constexpr (EPI == EPI_NCE_FWD) {
-        // s = alpha*acc with |s| <= alpha (unit-norm latents): exp(s - alpha) cannot overflow.
+        // Per row and column block: running maximum m and sum of 2^(x - m), x = s*log2(e), with an
+        // online rescale per 32-column chunk (no fixed shift: a fixed exp(s - alpha) underflows
+        // to sum = 0 once exp(temperature) reaches CLIP's usual logit scales of 50-100).
         const float alpha = __ldg(p.alpha_dev);
         const float a2 = alpha * 1.4426950408889634f;
         const int diag_col = row + p.diag_offset;
-        float rsum = 0.f;
+        float run_m = -INFINITY, run_s = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           const int col0 = n_blk * BLOCK_N + c * 32;
+          if (col0 >= p.N) break;
+          const bool interior = col0 + 32 <= p.N && (diag_col < col0 || diag_col >= col0 + 32);
+          float cm = -INFINITY;
+          if (interior) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = col0 + i;
-            const float acc_v = __uint_as_float(v[i]);
-            const bool is_diag = (col == diag_col);
-            if (is_diag && row_ok) p.nce_pos[row] = acc_v * alpha;
-            if (col < p.N && !(p.dcl && is_diag)) rsum += exp2f(acc_v * a2 - a2);
+            for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              const bool is_diag = (col == diag_col);
+              if (is_diag && row_ok) p.nce_pos[row] = __uint_as_float(v[i]) * alpha;
+              if (col >= p.N || (p.dcl && is_diag)) v[i] = 0xff800000u;   // -inf: not in the sum
+              cm = fmaxf(cm, __uint_as_float(v[i]));
+            }
+          }
+          cm *= a2;                                   // a2 > 0: max commutes with the scaling
+          if (cm > run_m) { run_s *= exp2f(run_m - cm); run_m = cm; }
+          if (run_m > -INFINITY) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) run_s += exp2f(fmaf(__uint_as_float(v[i]), a2, -run_m));
           }
         }
-        if (row_ok) p.nce_part[(long long)n_blk * p.M + row] = rsum;
+        if (row_ok) {
+          float2* dst = reinterpret_cast<float2*>(p.nce_part) + ((long long)n_blk * p.M + row);
+          *dst = make_float2(run_m, run_s);
+        }
       } else if constexpr (EPI == EPI_SEGMAX) {
         const float alpha = __ldg(p.alpha_dev);
         const int col_base = n_blk * n_stride;

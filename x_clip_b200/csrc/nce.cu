@@ -2,8 +2,8 @@
 // tcgen05 GEMM mainloop (gemm.cuh) with loss-specific epilogues:
 //
 //   forward  : s = exp(temperature) * A B^T is produced tile by tile in TMEM and immediately
-//              reduced to per-row partial sums of exp(s - alpha); the B_l x B_g logits matrix
-//              is never written.  A finalize kernel turns the partials into log-denominators
+//              reduced to per-row, per-column-block (running max, sum of exp(s - max)) pairs;
+//              the B_l x B_g logits matrix is never written.  A finalize kernel turns the partials into log-denominators
 //              and the loss contribution  scale * sum_r (lse_r - s_rr).
 //   backward : the same tiles are recomputed and turned into
 //              g = w_row*exp(s - lse_row) + w_col*exp(s - lse_col) - w_diag*[positive]
@@ -23,12 +23,17 @@ nce_finalize_kernel(const float* __restrict__ part, int nblk, const float* __res
                     int rows, const float* __restrict__ alpha_dev, float* __restrict__ lse,
                     float* __restrict__ loss_accum, float scale) {
   __shared__ float red[32];
-  const float alpha = __ldg(alpha_dev);
   float local = 0.f;
+  const float2* part2 = reinterpret_cast<const float2*>(part);
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    float m = -INFINITY;
+    for (int k = 0; k < nblk; ++k) m = fmaxf(m, part2[(long long)k * rows + r].x);
     float s = 0.f;
-    for (int k = 0; k < nblk; ++k) s += part[(long long)k * rows + r];
-    const float l = alpha + logf(s);
+    for (int k = 0; k < nblk; ++k) {
+      const float2 ps = part2[(long long)k * rows + r];
+      if (ps.x > -INFINITY) s += ps.y * exp2f(ps.x - m);
+    }
+    const float l = (m + log2f(s)) * 0.6931471805599453f;
     lse[r] = l;
     local += l - pos[r];
   }

@@ -253,7 +253,7 @@ def nce_fwd(a, b, temp_exp, diag_offset, dcl, loss_accum=None, loss_scale=0.0):
     R, D = a.shape
     C = b.shape[0]
     nblk = _lib.load().xclip_nce_num_col_blocks(C)
-    part = torch.empty((nblk, R), device=a.device, dtype=F32)
+    part = torch.empty((nblk, R, 2), device=a.device, dtype=F32)
     pos = torch.empty((R,), device=a.device, dtype=F32)
     lse = torch.empty((R,), device=a.device, dtype=F32)
     _call(a, "nce_fwd", 2.0 * R * C * D, 2.0 * (R + C) * D + 8.0 * R, "xclip_nce_fwd", a.data_ptr(), b.data_ptr(), R, C, D, temp_exp.data_ptr(),
