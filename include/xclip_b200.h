@@ -182,6 +182,15 @@ int xclip_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos,
 int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float* dpos, float* dcls,
                          int B, int n, int d, int vocab, xclip_stream_t stream);
 
+/* ---- rotary position embedding (x_clip/x_clip.py:155-176, applied to q, k and v at :221-223) ----
+ * In place on the bf16 qkv buffer [rows, ld] (rows = B*n tokens, position = row %% n): in each of
+ * the `nslices` consecutive 64-wide head slices the first 32 features are rotated pairwise
+ * (j with j+16) by angle[pos, j]; cos_tab / sin_tab f32 [n, 16].  inverse != 0: the transposed
+ * rotation (backward, applied to dq | dk | dv). */
+int xclip_rotary_inplace(void* qkv, int64_t ld, int64_t rows, int n, int nslices,
+                         const float* cos_tab, const float* sin_tab, int inverse,
+                         xclip_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,9 @@ class ClipConfig:
     use_all_token_embeds: bool = False
     decoupled_contrastive_learning: bool = False
     extra_latent_projection: bool = False
+    text_rotary_pos_emb: bool = False      # :428 - rotary instead of the absolute position table
+    text_causal_mask: bool = False         # :429 - causal text tower, no CLS token, EOS pooling
+    text_eos_id: Optional[int] = None      # :430
 
     def to_kwargs(self) -> dict:
         return dict(self.__dict__)
@@ -65,19 +68,44 @@ def gain_layernorm(x: Tensor, g: Tensor) -> Tensor:
     return (x - mu) * torch.rsqrt(var + eps) * g
 
 
+def rotary_angles(n_pos: int, rot_dim: int) -> Tensor:
+    """RotaryEmbedding(rot_dim)(n_pos) (:155-166): angle[pos, j] = pos / 10000^(2(j mod rot_dim/2)/rot_dim),
+    the half-table repeated twice along the feature axis -> [n_pos, rot_dim]."""
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, rot_dim, 2).float() / rot_dim))
+    ang = torch.arange(n_pos).float()[:, None] * inv_freq[None, :]
+    return torch.cat([ang, ang], dim=-1)
+
+
+def rotate_features(ang: Tensor, t: Tensor) -> Tensor:
+    """apply_rotary_pos_emb (:168-176): the first rot_dim features of every head are rotated
+    pairwise (feature j with j + rot_dim/2), the rest pass through."""
+    r = ang.shape[-1]
+    head, rest = t[..., :r], t[..., r:]
+    a, b = head[..., : r // 2], head[..., r // 2:]
+    turned = torch.cat([-b, a], dim=-1)
+    return torch.cat([head * ang.cos() + turned * ang.sin(), rest], dim=-1)
+
+
 def attention(x: Tensor, p: Params, prefix: str, heads: int, dim_head: int,
-              key_mask: Optional[Tensor]) -> Tensor:
-    """Bidirectional multi-head attention with a key-padding mask, followed by the output
-    projection AND a LayerNorm (:201-245).  q is pre-scaled by dim_head**-0.5 (:219);
-    masked keys are filled with -finfo.max, not -inf (:227-231); softmax in fp32 (:238)."""
+              key_mask: Optional[Tensor], causal: bool = False,
+              rotary: Optional[Tensor] = None) -> Tensor:
+    """Multi-head attention with a key-padding mask (and optionally a causal mask), followed by
+    the output projection AND a LayerNorm (:201-245).  q is pre-scaled by dim_head**-0.5 (:219);
+    rotary angles, when given, rotate q, k AND v (:221-223); masked keys are filled with
+    -finfo.max, not -inf (:227-236); softmax in fp32 (:238)."""
     b, n, _ = x.shape
     qkv = x @ p[prefix + "to_qkv.weight"].t()                       # [b, n, 3*h*dh]
     qkv = qkv.view(b, n, 3, heads, dim_head).permute(2, 0, 3, 1, 4)  # [3, b, h, n, dh]
     q, k, v = qkv[0] * dim_head ** -0.5, qkv[1], qkv[2]
+    if rotary is not None:
+        q, k, v = rotate_features(rotary, q), rotate_features(rotary, k), rotate_features(rotary, v)
     scores = q @ k.transpose(-1, -2)                                 # [b, h, n, n]
+    fill = -torch.finfo(scores.dtype).max
     if key_mask is not None:
-        fill = -torch.finfo(scores.dtype).max
         scores = torch.where(key_mask[:, None, None, :], scores, torch.full_like(scores, fill))
+    if causal:
+        future = torch.ones(n, n, dtype=torch.bool, device=x.device).triu(1)
+        scores = scores.masked_fill(future, fill)
     probs = torch.softmax(scores.float(), dim=-1).to(scores.dtype)
     ctx = (probs @ v).permute(0, 2, 1, 3).reshape(b, n, heads * dim_head)
     out = ctx @ p[prefix + "to_out.0.weight"].t()
@@ -96,14 +124,16 @@ def geglu_feedforward(x: Tensor, p: Params, prefix: str) -> Tensor:
 
 
 def transformer_stack(x: Tensor, p: Params, prefix: str, depth: int, heads: int, dim_head: int,
-                      key_mask: Optional[Tensor]) -> Tensor:
+                      key_mask: Optional[Tensor], causal: bool = False,
+                      rotary: Optional[Tensor] = None) -> Tensor:
     """norm_in -> depth x (pre-norm attention + residual, pre-norm feed-forward + residual)
     -> norm_out (:247-291)."""
     x = gain_layernorm(x, p[prefix + "norm_in.g"])
     for layer in range(depth):
         a = f"{prefix}layers.{layer}.0."
         f = f"{prefix}layers.{layer}.1."
-        x = attention(gain_layernorm(x, p[a + "norm.g"]), p, a + "fn.", heads, dim_head, key_mask) + x
+        x = attention(gain_layernorm(x, p[a + "norm.g"]), p, a + "fn.", heads, dim_head, key_mask,
+                      causal, rotary) + x
         x = geglu_feedforward(gain_layernorm(x, p[f + "norm.g"]), p, f + "fn.") + x
     return gain_layernorm(x, p[prefix + "norm_out.g"])
 
@@ -111,16 +141,36 @@ def transformer_stack(x: Tensor, p: Params, prefix: str, depth: int, heads: int,
 # --------------------------------------------------------------------------- encoders
 
 def encode_text(ids: Tensor, key_mask: Tensor, p: Params, cfg: ClipConfig) -> Tensor:
-    """Token + absolute position embedding, CLS prepended (always attendable), transformer
-    (:295-338).  Returns [b, 1+n, dim_text]."""
+    """Token embedding + absolute position table (or rotary angles for n+1 positions, :326-328),
+    CLS prepended and always attendable unless the tower is causal (:313, :330-335), transformer
+    (:295-338).  Returns [b, 1+n, dim_text] (causal: [b, n, dim_text])."""
     b, n = ids.shape
     x = p["text_transformer.token_emb.weight"][ids]
-    x = x + p["text_transformer.abs_pos_emb.weight"][:n][None]
-    cls = p["text_transformer.cls_token"].expand(b, 1, -1)
-    x = torch.cat([cls, x], dim=1)
-    mask = torch.cat([torch.ones(b, 1, dtype=torch.bool, device=ids.device), key_mask], dim=1)
+    rotary = None
+    if cfg.text_rotary_pos_emb:
+        rotary = rotary_angles(n + 1, min(cfg.text_dim_head, 32))
+    else:
+        x = x + p["text_transformer.abs_pos_emb.weight"][:n][None]
+    mask = key_mask
+    if not cfg.text_causal_mask:
+        cls = p["text_transformer.cls_token"].expand(b, 1, -1)
+        x = torch.cat([cls, x], dim=1)
+        mask = torch.cat([torch.ones(b, 1, dtype=torch.bool, device=ids.device), key_mask], dim=1)
     return transformer_stack(x, p, "text_transformer.transformer.", cfg.text_enc_depth,
-                             cfg.text_heads, cfg.text_dim_head, mask)
+                             cfg.text_heads, cfg.text_dim_head, mask, cfg.text_causal_mask, rotary)
+
+
+def eos_to_front(enc_text: Tensor, ids: Tensor, eos_id: int) -> Tensor:
+    """Causal text tower: the encoding at the FIRST eos token of every row becomes token 0, the
+    other tokens keep their order behind it (:668-685, with the undefined `b` read as the batch)."""
+    is_eos = ids == eos_id
+    assert bool(is_eos.any(dim=-1).all()), f"some of the text rows does not have the eos id {eos_id}"
+    first = is_eos.float().argmax(dim=-1)                                # [b]
+    b, n, d = enc_text.shape
+    pos = torch.arange(n, device=ids.device)[None, :].expand(b, -1)
+    rest = pos[pos != first[:, None]].view(b, n - 1)
+    order = torch.cat([first[:, None], rest], dim=1)                      # [b, n]
+    return torch.gather(enc_text, 1, order[:, :, None].expand(-1, -1, d))
 
 
 def patchify(img: Tensor, patch: int) -> Tensor:
@@ -217,6 +267,8 @@ def clip_forward(p: Params, text: Tensor, image: Tensor, cfg: ClipConfig,
     (:597-875 with the defaults of :444-454): loss weight of the contrastive term is 1."""
     mask = text != cfg.text_pad_id                                       # :614
     enc_t = encode_text(text, mask, p, cfg)
+    if cfg.text_causal_mask:
+        enc_t = eos_to_front(enc_t, text, cfg.text_eos_id)
     enc_i = encode_image(image, p, cfg, keep)
     zt, zi, zt_x, zi_x = project_latents(enc_t, enc_i, p, cfg)
     loss = contrastive_loss(zt, zi, zt_x, zi_x, p["temperature"], cfg, mask)
@@ -240,7 +292,10 @@ def clip_forward_sharded(p: Params, texts: Sequence[Tensor], images: Sequence[Te
         ctx = torch.enable_grad() if r == rank else torch.no_grad()
         with ctx:
             m = t != cfg.text_pad_id
-            z = project_latents(encode_text(t, m, p, cfg), encode_image(im, p, cfg), p, cfg)
+            et = encode_text(t, m, p, cfg)
+            if cfg.text_causal_mask:
+                et = eos_to_front(et, t, cfg.text_eos_id)
+            z = project_latents(et, encode_image(im, p, cfg), p, cfg)
         lat.append(z)
     cat = [torch.cat([z[j] for z in lat], dim=0) for j in range(4)]
     return contrastive_loss(cat[0], cat[1], cat[2], cat[3], p["temperature"], cfg)
@@ -267,9 +322,11 @@ def param_shapes(cfg: ClipConfig) -> Dict[str, Tuple[int, ...]]:
         s[prefix + "norm_in.g"] = (d,)
         s[prefix + "norm_out.g"] = (d,)
 
-    s["text_transformer.cls_token"] = (cfg.dim_text,)
+    if not cfg.text_causal_mask:                      # :313
+        s["text_transformer.cls_token"] = (cfg.dim_text,)
     s["text_transformer.token_emb.weight"] = (cfg.num_text_tokens, cfg.dim_text)
-    s["text_transformer.abs_pos_emb.weight"] = (cfg.text_seq_len, cfg.dim_text)
+    if not cfg.text_rotary_pos_emb:                   # :310
+        s["text_transformer.abs_pos_emb.weight"] = (cfg.text_seq_len, cfg.dim_text)
     tower("text_transformer.transformer.", cfg.dim_text, cfg.text_enc_depth, cfg.text_heads,
           cfg.text_dim_head)
     n_patch = (cfg.visual_image_size // cfg.visual_patch_size) ** 2
@@ -318,6 +375,18 @@ def protocol_inputs(cfg: ClipConfig, batch: int, seed: int, pad_fraction: float 
     if pad_fraction > 0:
         drop = torch.rand((batch, cfg.text_seq_len), generator=g) < pad_fraction
         text = text.masked_fill(drop, cfg.text_pad_id)
+    if cfg.text_causal_mask:
+        # every row needs an eos token (:670): one per row at a random position >= 1 (a second one
+        # later in half of the rows - the reference takes the first), never anywhere else
+        eos = cfg.text_eos_id
+        other = 1 if eos != 1 else 2
+        text = torch.where(text == eos, torch.full_like(text, other), text)
+        where = torch.randint(1, cfg.text_seq_len, (batch,), generator=g)
+        text[torch.arange(batch), where] = eos
+        again = torch.randint(1, cfg.text_seq_len, (batch,), generator=g)
+        for r in range(0, batch, 2):
+            if again[r] > where[r]:
+                text[r, again[r]] = eos
     image = torch.randn((batch, cfg.channels, cfg.visual_image_size, cfg.visual_image_size),
                         generator=g)
     return text, image

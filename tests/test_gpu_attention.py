@@ -72,7 +72,7 @@ def test_attn_bwd(cuda_device, B, n, H, masked):
         err = (dqkv[:, sl].float() - g[:, sl]).abs().max().item()
         sc = g[:, sl].abs().max().item()
         assert err <= 3e-2 * sc + 1e-6, f"{name}: err {err} vs scale {sc}"   # (n = 1: dq = dk = 0 exactly)
-        rel = (dqkv[:, sl].float() - g[:, sl]).norm().item() / (g[:, sl].norm().item() + 1e-6)
+        rel = (dqkv[:, sl].float() - g[:, sl]).norm().item() / (g[:, sl].norm().item() + 1e-3)
         assert rel < 1e-2, f"{name}: rel fro err {rel}"
 
 

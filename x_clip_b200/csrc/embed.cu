@@ -142,3 +142,77 @@ extern "C" int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* d
   XCLIP_LAUNCH_CHECK("text_embed_colsum_kernel");
   return XCLIP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Rotary position embedding of the text tower (x_clip/x_clip.py:155-176, applied to q, k AND v at
+// :221-223), in place on the bf16 qkv buffer right after the QKV projection.  The first 32
+// features of every 64-wide head slice are rotated pairwise (feature j with j+16) by the angle
+// pos * inv_freq[j]; cos/sin tables [n, 16] come from the caller (the module's inv_freq buffer).
+// inverse != 0 applies the transposed rotation: the backward of the same op on dq | dk | dv.
+namespace xclip {
+__global__ void __launch_bounds__(256)
+rotary_inplace_kernel(bf16* __restrict__ qkv, long long ld, long long rows, int n, int nslices,
+                      const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                      int inverse) {
+  const long long total = rows * nslices;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / nslices;
+    const int slice = (int)(idx - row * nslices);
+    const int pos = (int)(row % n);
+    bf16* ptr = qkv + row * ld + (long long)slice * 64;
+    uint4 raw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) raw[i] = reinterpret_cast<const uint4*>(ptr)[i];
+    float t[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        t[i * 8 + k * 2] = f.x;
+        t[i * 8 + k * 2 + 1] = f.y;
+      }
+    }
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float c = __ldg(cos_tab + pos * 16 + j);
+      const float s0 = __ldg(sin_tab + pos * 16 + j);
+      const float s = inverse ? -s0 : s0;
+      o[j] = t[j] * c - t[j + 16] * s;
+      o[j + 16] = t[j + 16] * c + t[j] * s;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 w;
+      w.x = pack_bf16x2(o[i * 8 + 0], o[i * 8 + 1]);
+      w.y = pack_bf16x2(o[i * 8 + 2], o[i * 8 + 3]);
+      w.z = pack_bf16x2(o[i * 8 + 4], o[i * 8 + 5]);
+      w.w = pack_bf16x2(o[i * 8 + 6], o[i * 8 + 7]);
+      reinterpret_cast<uint4*>(ptr)[i] = w;
+    }
+  }
+}
+}  // namespace xclip
+
+extern "C" int xclip_rotary_inplace(void* qkv, int64_t ld, int64_t rows, int n, int nslices,
+                                    const float* cos_tab, const float* sin_tab, int inverse,
+                                    xclip_stream_t stream) {
+  using namespace xclip;
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(qkv && cos_tab && sin_tab, "rotary: null pointer");
+  XCLIP_REQUIRE(rows > 0 && n > 0 && nslices > 0 && rows % n == 0, "rotary: bad sizes");
+  XCLIP_REQUIRE(ld % 8 == 0 && ld >= (int64_t)nslices * 64 &&
+                    (reinterpret_cast<uintptr_t>(qkv) & 15) == 0,
+                "rotary: qkv must be 16-byte aligned with ld %% 8 == 0");
+  const long long total = (long long)rows * nslices;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  rotary_inplace_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<bf16*>(qkv), ld, rows, n, nslices, cos_tab, sin_tab, inverse);
+  XCLIP_LAUNCH_CHECK("rotary_inplace_kernel");
+  return XCLIP_OK;
+}

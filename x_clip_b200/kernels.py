@@ -246,6 +246,18 @@ def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale, causal=False):
     return dqkv
 
 
+def rotary_(qkv, n, nslices, cos_tab, sin_tab, inverse=False):
+    """In-place rotary embedding of the q | k | v head slices (see xclip_rotary_inplace)."""
+    _need(qkv, BF16, "qkv"); _rows2d(qkv, "qkv"); _need(cos_tab, F32, "cos"); _need(sin_tab, F32, "sin")
+    if tuple(cos_tab.shape) != (n, 16) or tuple(sin_tab.shape) != (n, 16) or not (
+            cos_tab.is_contiguous() and sin_tab.is_contiguous()):
+        raise _lib.XClipB200Error("rotary: cos/sin tables must be contiguous [n, 16]")
+    _call(qkv, "rotary", 0.0, 4.0 * qkv.shape[0] * nslices * 32, "xclip_rotary_inplace", qkv.data_ptr(),
+          qkv.stride(0), qkv.shape[0], int(n), int(nslices), cos_tab.data_ptr(), sin_tab.data_ptr(),
+          1 if inverse else 0)
+    return qkv
+
+
 def nce_fwd(a, b, temp_exp, diag_offset, dcl, loss_accum=None, loss_scale=0.0):
     """Row-block InfoNCE forward: (lse [R], pos [R]) for rows a vs all columns b.
     temp_exp: fp32 DEVICE scalar tensor holding exp(temperature)."""
