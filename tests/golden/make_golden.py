@@ -59,7 +59,11 @@ CASES = {
     "vitb16_shaped_drop": (dict(VITB16_2L), 4, 0.1, 0.5),     # image attention n = 98 (cfg3 bench shape)
     "filip_t256": (dict(FILIP_T256), 3, 0.3, 0.0),            # T = 256, I = 64
     "filip_t256_drop": (dict(FILIP_T256), 3, 0.3, 0.5),       # T = 256, I = 32
-    "tiny_b64": (dict(TINY), 64, 0.2, 0.0),                   # batch large enough for the 1e-2 d temperature gate
+    "tiny_b64": (dict(TINY), 64, 0.2, 0.0),
+    # text-tower variants: rotary embedding on q, k AND v; causal mask + EOS pooling
+    "tiny_rotary": (dict(TINY, text_rotary_pos_emb=True), 6, 0.2, 0.0),
+    "tiny_causal": (dict(TINY, text_causal_mask=True, text_eos_id=5), 6, 0.2, 0.0),
+    "text77_causal": (dict(VITB16_2L, text_causal_mask=True, text_eos_id=999, visual_enc_depth=1), 4, 0.1, 0.5),                   # batch large enough for the 1e-2 d temperature gate
 }
 WEIGHT_SEED = 1234
 INPUT_SEED = 4321
@@ -82,8 +86,17 @@ def summ(t: torch.Tensor) -> dict:
 
 def build_reference(x_clip, cfg_kwargs, patch_dropout, state):
     clip = x_clip.CLIP(**cfg_kwargs, visual_patch_dropout=patch_dropout)
-    missing = clip.load_state_dict(state, strict=True)
+    full = dict(state)
+    for k, v in clip.state_dict().items():        # non-parameter buffers (rotary inv_freq) keep their own values
+        if k not in full:
+            assert k.endswith("inv_freq"), k
+            full[k] = v
+    clip.load_state_dict(full, strict=True)
     clip.train()
+    # text_causal_mask=True reads an undefined name `b` (x_clip.py:683) where the batch size is meant
+    # (SURVEY.md 8c): supply it as a module global - the reference source itself stays untouched
+    import x_clip.x_clip as _xc
+    _xc.b = None
     return clip
 
 
@@ -99,6 +112,8 @@ def run_case(x_clip, name, cfg_kwargs, batch, pad_fraction, patch_dropout):
         k = max(1, int(n * (1 - patch_dropout)))
         torch.manual_seed(DROP_SEED)
         keep = torch.randn(batch, n).topk(k, dim=-1).indices   # PatchDropout's draw (x_clip.py:149)
+    import x_clip.x_clip as _xc
+    _xc.b = batch                                  # see build_reference()
     torch.manual_seed(DROP_SEED)
     loss = clip(text, image, return_loss=True)
     loss.backward()

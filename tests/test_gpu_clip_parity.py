@@ -20,7 +20,9 @@ TINY_CASES = ["tiny_plain", "tiny_nomask", "tiny_dcl", "tiny_extra", "tiny_dcl_e
               "tiny_filip", "tiny_filip_dcl_extra",
               # BASELINE cfg3-shaped towers at depth 2 (d_image 768, 12 heads, n = 196 / 98 image tokens,
               # 78 text tokens) and cfg4's FILIP token counts (T = 256, I = 64 / 32)
-              "vitb16_shaped", "vitb16_shaped_drop", "filip_t256", "filip_t256_drop"]
+              "vitb16_shaped", "vitb16_shaped_drop", "filip_t256", "filip_t256_drop",
+              # text-tower variants: rotary embedding (q, k and v), causal mask + EOS pooling
+              "tiny_rotary", "tiny_causal", "text77_causal"]
 
 
 def _run(case, dev):
@@ -33,7 +35,8 @@ def _run(case, dev):
     keep = None if gold["keep"] is None else torch.tensor(gold["keep"])
 
     clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=gold["patch_dropout"]).to(dev)
-    clip.load_state_dict(state, strict=True)
+    missing = clip.load_state_dict(state, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith("inv_freq") for k in missing.missing_keys), missing
     clip.train()
     if keep is not None:
         clip.visual_transformer.patch_dropout.forced_keep = keep

@@ -36,13 +36,25 @@ def test_unknown_kwargs_swallowed_and_asserts_kept():
         x_clip_b200.CLIP(**TINY, text_causal_mask=True)          # eos id missing (x_clip.py:480)
 
 
-@pytest.mark.parametrize("kw", [dict(use_mlm=True), dict(use_visual_ssl=True), dict(text_rotary_pos_emb=True),
+@pytest.mark.parametrize("kw", [dict(use_mlm=True), dict(use_visual_ssl=True),
                                 dict(text_dim_head=32), dict(dim_text=320), dict(sim_reg_loss_weight=0.1),
                                 dict(downsample_image_embeds=True, use_all_token_embeds=True),
-                                dict(text_causal_mask=True, text_eos_id=1)])
+                                # rotary + causal is broken in the reference itself (x_clip.py:328)
+                                dict(text_causal_mask=True, text_eos_id=1, text_rotary_pos_emb=True),
+                                # the causal kernels cover <= 128 tokens
+                                dict(text_causal_mask=True, text_eos_id=1, text_seq_len=256)])
 def test_unsupported_flags_raise_at_construction(kw):
     with pytest.raises(x_clip_b200.Unsupported):
         x_clip_b200.CLIP(**{**TINY, **kw})
+
+
+def test_rotary_and_causal_towers_mirror_the_reference_parameter_tree():
+    from oracle import clip_oracle as O
+    for kw in (dict(text_rotary_pos_emb=True), dict(text_causal_mask=True, text_eos_id=5)):
+        clip = x_clip_b200.CLIP(**{**TINY, **kw})
+        want = set(O.param_shapes(O.ClipConfig(**{**TINY, **kw})).keys())
+        got = set(clip.state_dict().keys())
+        assert got - want <= {"text_transformer.rotary_pos_emb.inv_freq"} and not (want - got), (kw, got ^ want)
 
 
 def test_cpu_inputs_fail_loudly():

@@ -7,8 +7,9 @@ working.  The modules here are parameter CONTAINERS: all arithmetic on the hot p
 done by the CUDA kernels behind include/xclip_b200.h, scheduled by x_clip_b200.engine.
 
 Feature combinations the kernels do not cover raise at construction (never a silent CPU or
-eager fallback): dim_head != 64, model dims not multiples of 256, rotary embeddings, causal
-text mask, dropout > 0, MLM / visual SSL / multiview / similarity-regularisation terms and
+eager fallback): dim_head != 64, model dims not multiples of 256, a causal text tower longer than
+128 tokens, rotary + causal together (broken in the reference itself: n+1 angles for n tokens,
+x_clip.py:328), dropout > 0, MLM / visual SSL / multiview / similarity-regularisation terms and
 conv-downsampled image latents.
 """
 from __future__ import annotations
@@ -62,10 +63,9 @@ class Attention(nn.Module):
                  dropout: float = 0.):
         super().__init__()
         _require(dim_head == 64, f"dim_head must be 64, got {dim_head}")
-        _require(not causal, "causal attention is not implemented (the reference path itself is "
-                             "broken, SURVEY.md 8c)")
         _require(dropout == 0., "attention dropout > 0 is not implemented")
         self.heads = heads
+        self.causal = causal
         self.scale = dim_head ** -0.5
         inner = dim_head * heads
         self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
@@ -96,7 +96,7 @@ class Transformer(nn.Module):
         super().__init__()
         _require(dim % 256 == 0 and dim <= 1024, f"model dim must be 256/512/768/1024, got {dim}")
         _require(depth >= 1, "depth must be >= 1")
-        self.dim, self.depth, self.heads = dim, depth, heads
+        self.dim, self.depth, self.heads, self.causal = dim, depth, heads, causal
         # activation checkpointing only trades memory for recompute; accepted and ignored
         self.checkpoint_during_training = checkpoint_during_training
         self.layers = nn.ModuleList([
@@ -117,9 +117,19 @@ class Transformer(nn.Module):
         return w
 
     def forward(self, x, rotary_pos_emb=None, mask=None):
-        _require(rotary_pos_emb is None, "rotary position embedding is not implemented")
+        """rotary_pos_emb: the reference's angle table [n, 32] (RotaryEmbedding.forward, :161-166);
+        its two halves are equal, the kernel takes cos / sin of the first 16 columns."""
         _require(x.is_cuda, "inputs must live on a CUDA (sm_100) device")
-        return E.TransformerFn.apply(x, mask, self.heads, self.depth, *self.flat_weights())
+        n = x.shape[1]
+        _require(not self.causal or n <= 128, "the causal mask is implemented for sequences <= 128 tokens")
+        cos = sin = None
+        if rotary_pos_emb is not None:
+            _require(tuple(rotary_pos_emb.shape) == (n, 32),
+                     f"rotary table must be [n, 32] (dim_head 64 -> rot dim 32), got {tuple(rotary_pos_emb.shape)}")
+            ang = rotary_pos_emb[:, :16].to(device=x.device, dtype=torch.float32)
+            cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+        return E.TransformerFn.apply(x, mask, self.heads, self.depth, self.causal, cos, sin,
+                                     *self.flat_weights())
 
 
 class PatchDropout(nn.Module):
@@ -144,26 +154,57 @@ class PatchDropout(nn.Module):
         return torch.gather(x, 1, idx[:, :, None].expand(-1, -1, d))
 
 
+class RotaryEmbedding(nn.Module):
+    """Angle table of the rotary embedding (reference :155-166); `inv_freq` is a buffer so that
+    reference checkpoints load unchanged."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.register_buffer('inv_freq', 1. / (10000 ** (torch.arange(0, dim, 2).float() / dim)))
+
+    def forward(self, seq_len: int, device):
+        t = torch.arange(seq_len, device=device).type_as(self.inv_freq)
+        freqs = torch.einsum('i , j -> i j', t, self.inv_freq.to(device))
+        return torch.cat((freqs, freqs), dim=-1)
+
+
 class TextTransformer(nn.Module):
     def __init__(self, dim: int, *, num_tokens: int, max_seq_len: int, dim_head: int,
                  rotary_pos_emb=None, causal: bool = False, **kwargs):
         super().__init__()
-        _require(not rotary_pos_emb, "text_rotary_pos_emb is not implemented")
-        _require(not causal, "text_causal_mask is not implemented")
+        _require(not (rotary_pos_emb and causal),
+                 "text_rotary_pos_emb with text_causal_mask is broken in the reference itself "
+                 "(n+1 rotary positions for n tokens, x_clip.py:328) and not offered here")
         _require(max_seq_len + 1 <= 320, "text_seq_len + CLS must be <= 320 tokens")
+        _require(not causal or max_seq_len <= 128, "text_causal_mask needs text_seq_len <= 128")
         self.token_emb = nn.Embedding(num_tokens, dim)
-        self.abs_pos_emb = nn.Embedding(max_seq_len, dim)
-        self.cls_token = nn.Parameter(torch.randn(dim))
+        self.abs_pos_emb = nn.Embedding(max_seq_len, dim) if not rotary_pos_emb else None
+        self.rotary_pos_emb = RotaryEmbedding(min(dim_head, 32)) if rotary_pos_emb else None
+        self.cls_token = nn.Parameter(torch.randn(dim)) if not causal else None
+        self.max_seq_len = max_seq_len
         self.transformer = Transformer(dim, dim_head=dim_head, causal=causal, **kwargs)
 
     def forward(self, x, mask=None):
         b, n = x.shape
         _require(x.is_cuda, "inputs must live on a CUDA (sm_100) device")
-        _require(n <= self.abs_pos_emb.num_embeddings, "text longer than text_seq_len")
-        h = E.TextEmbedFn.apply(x, self.token_emb.weight, self.abs_pos_emb.weight, self.cls_token)
-        if mask is not None:
+        _require(n <= self.max_seq_len, "text longer than text_seq_len")
+        rotary = None
+        if self.abs_pos_emb is not None and self.cls_token is not None:
+            # default configuration: gather + position + CLS in one kernel
+            h = E.TextEmbedFn.apply(x, self.token_emb.weight, self.abs_pos_emb.weight, self.cls_token)
+        else:
+            # rotary (no position table) or causal (no CLS token): plain embedding lookups
+            h = self.token_emb(x)
+            if self.abs_pos_emb is not None:
+                h = h + self.abs_pos_emb(torch.arange(n, device=x.device))[None]
+            if self.rotary_pos_emb is not None:
+                rotary = self.rotary_pos_emb(n + 1, x.device)       # n + 1: the CLS position (:328)
+            if self.cls_token is not None:
+                h = torch.cat((self.cls_token.expand(b, 1, -1), h), dim=1)
+            h = h.to(BF16)
+        if mask is not None and self.cls_token is not None:
             mask = torch.cat((torch.ones(b, 1, dtype=torch.bool, device=mask.device), mask), dim=1)
-        return self.transformer(h, mask=mask)
+        return self.transformer(h, rotary_pos_emb=rotary, mask=mask)
 
 
 class VisionTransformer(nn.Module):
@@ -269,7 +310,6 @@ class CLIP(nn.Module):
                  "visual SSL (SimSiam/SimCLR) is outside the accelerated hot path")
         _require(not downsample_image_embeds, "downsample_image_embeds is not implemented")
         _require(sim_reg_loss_weight == 0., "sim_reg_loss_weight > 0 is not implemented")
-        _require(not text_causal_mask, "text_causal_mask is not implemented")
         _require(dim_latent % 256 == 0 and dim_latent <= 1024, "dim_latent must be 256/512/768/1024")
         _require(dim_text % 8 == 0 and dim_image % 8 == 0, "dim_text / dim_image must be multiples of 8")
 
@@ -326,10 +366,25 @@ class CLIP(nn.Module):
         self.has_sim_reg_loss = False
 
     # -- helpers ---------------------------------------------------------------------
+    def _eos_to_front(self, enc_text, text):
+        """Causal text tower: the encoding at the first EOS token of every row moves to index 0,
+        the others keep their order (reference :668-685; its undefined `b` is the batch size)."""
+        eos = text == self.text_eos_id
+        assert torch.all(torch.any(eos, dim=-1)), \
+            f'some of the text rows does not have the eos id {self.text_eos_id}'
+        b, n, d = enc_text.shape
+        first = eos.float().argmax(dim=-1, keepdim=True)                       # [b, 1]
+        pos = torch.arange(n, device=text.device)[None].expand(b, -1)
+        rest = pos[pos != first].view(b, n - 1)
+        order = torch.cat((first, rest), dim=1)
+        return torch.gather(enc_text, 1, order[:, :, None].expand(-1, -1, d))
+
     def _encode_to_latents(self, text, image, text_mask):
         """encoders -> CLS select -> projections (CLS mode).  Returns ([zt, zi(, zt_x, zi_x)], ops)."""
         text_args = (text,) if self.text_encode_without_mask else (text, text_mask)
         enc_text = self.text_transformer(*text_args)
+        if self.text_causal_mask:
+            enc_text = self._eos_to_front(enc_text, text)
         enc_image = self.visual_transformer(image)
         te = enc_text[:, 0] if enc_text.ndim == 3 else enc_text
         ie = enc_image[:, 0] if enc_image.ndim == 3 else enc_image
@@ -376,6 +431,8 @@ class CLIP(nn.Module):
                                              self.temperature)
         text_args = (text,) if self.text_encode_without_mask else (text, text_mask)
         enc_text = _encode(self.text_transformer, text_args, freeze_text_encoder)
+        if self.text_causal_mask:
+            enc_text = self._eos_to_front(enc_text, text)
         enc_image = _encode(self.visual_transformer, (image,), freeze_image_encoder)
 
         if return_encodings:

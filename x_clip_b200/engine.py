@@ -110,10 +110,12 @@ class TransformerFn(torch.autograd.Function):
     """x[B,n,d] (bf16) -> norm_out(blocks(norm_in(x))) (bf16); mask: bool [B,n] or None.
 
     flat weights = [norm_in.g, norm_out.g] + depth * [g1, wqkv, wo, go, g2, w1, g4, w2].
+    causal: the reference's causal mask (x_clip.py:233-236); rot_cos / rot_sin: f32 [n, 16] tables of
+    the rotary embedding applied to q, k and v (x_clip.py:221-223) or None.
     """
 
     @staticmethod
-    def forward(ctx, x, mask, heads: int, depth: int, *weights):
+    def forward(ctx, x, mask, heads: int, depth: int, causal: bool, rot_cos, rot_sin, *weights):
         B, n, d = x.shape
         M = B * n
         scale = 64 ** -0.5
@@ -133,7 +135,9 @@ class TransformerFn(torch.autograd.Function):
         for L, (g1, wqkv, wo, go, g2, w1, g4, w2) in enumerate(layers):
             bqkv, bo, b1, b2 = wb[L]
             qkv = K.gemm(xn, bqkv)
-            o, lse = K.attn_fwd(qkv, mask_c, B, n, heads, scale)
+            if rot_cos is not None:
+                K.rotary_(qkv, n, 3 * heads, rot_cos, rot_sin)
+            o, lse = K.attn_fwd(qkv, mask_c, B, n, heads, scale, causal)
             y = K.gemm(o, bo)
             # x1 = LN(y)*go + x ; xn2 = LN(x1)*g2   (attention tail + feed-forward pre-norm)
             x1, st_y, xn2, st_x1 = K.layernorm_fwd(y, go, res=xcur, g2=g2, eps=LN_EPS)
@@ -149,14 +153,16 @@ class TransformerFn(torch.autograd.Function):
         ctx.saved = saved
         ctx.tail = (x_in, st_in, xcur, st_out)
         ctx.mask = mask_c
-        ctx.dims = (B, n, d, heads, depth, scale)
+        ctx.dims = (B, n, d, heads, depth, scale, causal)
+        ctx.rot = (rot_cos, rot_sin)
         ctx.weights = weights
         ctx.wb = wb
         return out.view(B, n, d)
 
     @staticmethod
     def backward(ctx, dout):
-        B, n, d, heads, depth, scale = ctx.dims
+        B, n, d, heads, depth, scale, causal = ctx.dims
+        rot_cos, rot_sin = ctx.rot
         M = B * n
         weights = ctx.weights
         g_in, g_out = weights[0], weights[1]
@@ -198,7 +204,9 @@ class TransformerFn(torch.autograd.Function):
             grads[base + 3] = dgo
             d_o = K.gemm(dy, bo, b_major=1)
             grads[base + 2] = wg.wgrad(dy, o)
-            dqkv = K.attn_bwd(qkv, ctx.mask, o, d_o, lse, B, n, heads, scale)
+            dqkv = K.attn_bwd(qkv, ctx.mask, o, d_o, lse, B, n, heads, scale, causal)
+            if rot_cos is not None:      # back through the rotation (its transpose)
+                K.rotary_(dqkv, n, 3 * heads, rot_cos, rot_sin, inverse=True)
             dxn = K.gemm(dqkv, bqkv, b_major=1)
             grads[base + 1] = wg.wgrad(dqkv, xn)
             dg1 = torch.zeros(d, device=dev, dtype=F32)
@@ -209,7 +217,7 @@ class TransformerFn(torch.autograd.Function):
         grads[0] = dg_in
         wg.join()
         ctx.saved = ctx.wb = None
-        return (dx_in.view(B, n, d), None, None, None, *grads)
+        return (dx_in.view(B, n, d), None, None, None, None, None, None, *grads)
 
 
 class TextEmbedFn(torch.autograd.Function):
