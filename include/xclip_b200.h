@@ -59,6 +59,10 @@ void xclip_launch_count_reset(void);
  * Requirements: N % 8 == 0, lda/ldb/ldr % 8 == 0, ldc % 8 == 0 (bf16) or % 4 (f32),
  * 16-byte aligned base pointers.  bias is f32, residual is bf16.
  */
+/* 256-wide problems run on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) by default;
+ * xclip_gemm_set_pair_mode(0) selects the single-CTA 128 x 256 kernel instead (returns the
+ * previous setting).  Same results either way - a tuning / A-B switch, process-wide. */
+int xclip_gemm_set_pair_mode(int enabled);
 int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb,
                     int b_major, void* c, int64_t ldc, int c_dtype, int M, int N, int K,
                     float alpha, const float* bias, const void* residual, int64_t ldr,

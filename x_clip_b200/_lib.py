@@ -28,6 +28,7 @@ SIGNATURES = {
     "xclip_init": (c_int, []),
     "xclip_launch_count": (c_longlong, []),
     "xclip_launch_count_reset": (None, []),
+    "xclip_gemm_set_pair_mode": (c_int, [c_int]),
     "xclip_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
                                 c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_void_p]),

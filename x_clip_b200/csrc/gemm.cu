@@ -31,7 +31,37 @@ static int dispatch_major(int a_major, int b_major, const CUtensorMap& tmA, cons
   return launch_gemm<BLOCK_N, kMajorMN, kMajorMN>(tmA, tmB, tmC, p, grid, stream);
 }
 
+template <int A_MAJOR, int B_MAJOR>
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                            const GemmParams& p, int pairs, cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<A_MAJOR, B_MAJOR>;
+  const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Gemm2Smem::kTotal);
+  if (rc_attr) return rc_attr;
+  kern<<<2 * pairs, kGemmThreads, Gemm2Smem::kTotal, stream>>>(tmA, tmB, tmC, p);   // __cluster_dims__(2,1,1)
+  XCLIP_LAUNCH_CHECK("gemm2_bf16_kernel");
+  return XCLIP_OK;
+}
+
+static int dispatch_pair(int a_major, int b_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const CUtensorMap& tmC, const GemmParams& p, int pairs, cudaStream_t stream) {
+  if (a_major == kMajorK && b_major == kMajorK)
+    return launch_gemm_pair<kMajorK, kMajorK>(tmA, tmB, tmC, p, pairs, stream);
+  if (a_major == kMajorK && b_major == kMajorMN)
+    return launch_gemm_pair<kMajorK, kMajorMN>(tmA, tmB, tmC, p, pairs, stream);
+  if (a_major == kMajorMN && b_major == kMajorK)
+    return launch_gemm_pair<kMajorMN, kMajorK>(tmA, tmB, tmC, p, pairs, stream);
+  return launch_gemm_pair<kMajorMN, kMajorMN>(tmA, tmB, tmC, p, pairs, stream);
+}
+
+static int g_pair_mode = 1;
+
 }  // namespace xclip
+
+extern "C" int xclip_gemm_set_pair_mode(int enabled) {
+  const int prev = xclip::g_pair_mode;
+  xclip::g_pair_mode = enabled ? 1 : 0;
+  return prev;
+}
 
 extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb,
                                int b_major, void* c, int64_t ldc, int c_dtype, int M, int N, int K,
@@ -64,6 +94,9 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
   if (bias) XCLIP_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias misaligned");
 
   const int block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  // CTA-pair kernel (256 x 256 tiles, see gemm.cuh): whenever the single-CTA kernel would use 256-wide
+  // tiles and there are at least two 128-row blocks to pair up
+  const bool use_pair = g_pair_mode && block_n == 256 && M > kGemmBlockM;
 
   CUtensorMap tmA, tmB;
   if (a_major == 0) {
@@ -73,23 +106,26 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
   }
   if (rc) return rc;
   if (b_major == 0) {
-    rc = encode_2d_bf16(&tmB, b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)block_n);
+    rc = encode_2d_bf16(&tmB, b, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64,
+                        use_pair ? 128u : (uint32_t)block_n);
   } else {
     rc = encode_2d_bf16(&tmB, b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kGemmBlockK);
   }
   if (rc) return rc;
 
-  const int num_m = (M + kGemmBlockM - 1) / kGemmBlockM;
+  const int tile_m = use_pair ? 2 * kGemmBlockM : kGemmBlockM;
+  const int units = use_pair ? num_sms() / 2 : num_sms();      // CTAs or CTA pairs that run concurrently
+  const int num_m = (M + tile_m - 1) / tile_m;
   const int num_n = (N + block_n - 1) / block_n;
   const int num_kb = (K + kGemmBlockK - 1) / kGemmBlockK;
   const long long tiles_mn = (long long)num_m * num_n;
   int splits = 1;
-  if (accumulate && tiles_mn < num_sms()) {
+  if (accumulate && tiles_mn < units) {
     // wgrad-shaped problem: few output tiles, very long K.  Split K so that the CTAs form whole
     // waves over the SMs: among split counts that give between ~2 and ~8 waves (and keep >= 8
     // k-blocks per split to amortise the fp32 reduction) take the one with the best last-wave
     // fill; e.g. 64 output tiles: 5 splits = 2.16 waves (72 % fill) vs 9 splits = 3.89 (97 %).
-    const long long sms = num_sms();
+    const long long sms = units;
     const long long lo = (2 * sms + tiles_mn - 1) / tiles_mn;
     long long hi = (8 * sms) / tiles_mn;
     const long long max_by_k = num_kb / 8 > 0 ? num_kb / 8 : 1;
@@ -107,7 +143,7 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
     splits = (num_kb + kb_per - 1) / kb_per;  // no empty splits
   }
   const long long total_tiles = tiles_mn * splits;
-  int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  int grid = (int)(total_tiles < units ? total_tiles : units);
 
   GemmParams p = {};
   p.M = M; p.N = N; p.K = K;
@@ -122,6 +158,7 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
     p.use_tma_store = 1;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pair) return dispatch_pair(a_major, b_major, tmA, tmB, tmC, p, grid, s);
   if (block_n == 256) return dispatch_major<256>(a_major, b_major, tmA, tmB, tmC, p, grid, s);
   return dispatch_major<128>(a_major, b_major, tmA, tmB, tmC, p, grid, s);
 }

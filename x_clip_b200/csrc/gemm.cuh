@@ -79,6 +79,157 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
 };
 
+// Epilogue of one 128 x BLOCK_N accumulator tile (EPI_STORE): C = alpha*acc (+bias) (+residual) as
+// bf16 through swizzled smem staging + TMA stores, or fp32 direct / atomic.  Called by the four
+// epilogue warps (warp = 0..3 owns TMEM lanes 32*warp..+31); `store_count` is the running parity of
+// the two staging buffers.
+template <int BLOCK_N>
+__device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, const CUtensorMap& tmC,
+                                                    uint8_t* smem_c, uint32_t taddr, int warp,
+                                                    int lane, int m_blk, int n_blk, int split,
+                                                    uint32_t& store_count) {
+  const int row = m_blk * kGemmBlockM + warp * 32 + lane;
+  const bool row_ok = row < p.M;
+  const bf16* res_row = nullptr;
+  if (p.residual != nullptr && row_ok) {
+    const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    res_row = p.residual + rr * p.ldr;
+  }
+        if (p.use_tma_store) {
+          // bf16 output: 64-column boxes staged in swizzled smem (double buffered), written by
+          // cp.async.bulk.tensor stores (full-line writes, no LSU pressure, tails clipped by TMA)
+          const int row_in_tile = warp * 32 + lane;
+#pragma unroll 1
+          for (int q = 0; q < BLOCK_N / 64; ++q) {
+            const uint32_t stg = smem_u32(smem_c) + (store_count & 1) * 16384;
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int c32 = 0; c32 < 2; ++c32) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + q * 64 + c32 * 32, v);
+              tmem_ld_wait();
+              const int col0 = n_blk * BLOCK_N + q * 64 + c32 * 32;
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (col0 + i < p.N) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+                    f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                  }
+                }
+              }
+              if (res_row != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  if (col0 + i < p.N) {
+                    const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
+                    float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
+                    float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+                    f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
+                    f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                 stg + swz128(row_in_tile, c32 * 4 + i)),
+                             "r"(pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1])),
+                             "r"(pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3])),
+                             "r"(pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5])),
+                             "r"(pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]))
+                             : "memory");
+              }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
+              const int c0 = n_blk * BLOCK_N + q * 64;
+              if (c0 < p.N) {
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                        reinterpret_cast<uint64_t>(&tmC)),
+                    "r"(stg), "r"(c0), "r"(m_blk * kGemmBlockM)
+                    : "memory");
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++store_count;
+          }
+        } else {
+  #pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          if (row_ok && col0 < p.N) {
+            float f[32];
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+            if (p.bias != nullptr && split == 0) {
+  #pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (col0 + i < p.N) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+                  f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                }
+              }
+            }
+            if (res_row != nullptr && split == 0) {
+  #pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {
+                  const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
+                  float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
+                  float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+                  f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
+                  f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
+                }
+              }
+            }
+            if (p.c_is_f32) {
+              float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+              if (p.atomic_add) {
+  #pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (col0 + i < p.N) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i),
+                                 "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
+                                 : "memory");
+                  }
+                }
+              } else {
+  #pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  if (col0 + i < p.N)
+                    *reinterpret_cast<float4*>(crow + i) =
+                        make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                }
+              }
+            } else {
+              bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
+  #pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {
+                  uint4 o;
+                  o.x = pack_bf16x2(f[i], f[i + 1]);
+                  o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+                  o.z = pack_bf16x2(f[i + 4], f[i + 5]);
+                  o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(crow + i) = o;
+                }
+              }
+            }
+          }
+        }
+        }
+}
+
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -241,139 +392,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         res_row = p.residual + rr * p.ldr;
       }
       if constexpr (EPI == EPI_STORE) {
-        if (p.use_tma_store) {
-          // bf16 output: 64-column boxes staged in swizzled smem (double buffered), written by
-          // cp.async.bulk.tensor stores (full-line writes, no LSU pressure, tails clipped by TMA)
-          const int row_in_tile = warp * 32 + lane;
-#pragma unroll 1
-          for (int q = 0; q < BLOCK_N / 64; ++q) {
-            const uint32_t stg = smem_u32(smem_c) + (store_count & 1) * 16384;
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-            for (int c32 = 0; c32 < 2; ++c32) {
-              uint32_t v[32];
-              tmem_ld_32x32(taddr + q * 64 + c32 * 32, v);
-              tmem_ld_wait();
-              const int col0 = n_blk * BLOCK_N + q * 64 + c32 * 32;
-              float f[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-              if (p.bias != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  if (col0 + i < p.N) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
-                    f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-                  }
-                }
-              }
-              if (res_row != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  if (col0 + i < p.N) {
-                    const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
-                    float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
-                    float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
-                    f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
-                    f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
-                  }
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
-                                 stg + swz128(row_in_tile, c32 * 4 + i)),
-                             "r"(pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1])),
-                             "r"(pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3])),
-                             "r"(pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5])),
-                             "r"(pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]))
-                             : "memory");
-              }
-            }
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 0) {
-              const int c0 = n_blk * BLOCK_N + q * 64;
-              if (c0 < p.N) {
-                asm volatile(
-                    "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                        reinterpret_cast<uint64_t>(&tmC)),
-                    "r"(stg), "r"(c0), "r"(m_blk * kGemmBlockM)
-                    : "memory");
-              }
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            ++store_count;
-          }
-        } else {
-  #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = n_blk * BLOCK_N + c * 32;
-          if (row_ok && col0 < p.N) {
-            float f[32];
-  #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-            if (p.bias != nullptr && split == 0) {
-  #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                if (col0 + i < p.N) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + i);
-                  f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-                }
-              }
-            }
-            if (res_row != nullptr && split == 0) {
-  #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (col0 + i < p.N) {
-                  const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
-                  float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y);
-                  float2 cc = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
-                  f[i] += a.x; f[i + 1] += a.y; f[i + 2] += b.x; f[i + 3] += b.y;
-                  f[i + 4] += cc.x; f[i + 5] += cc.y; f[i + 6] += d.x; f[i + 7] += d.y;
-                }
-              }
-            }
-            if (p.c_is_f32) {
-              float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
-              if (p.atomic_add) {
-  #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  if (col0 + i < p.N) {
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i),
-                                 "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
-                                 : "memory");
-                  }
-                }
-              } else {
-  #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  if (col0 + i < p.N)
-                    *reinterpret_cast<float4*>(crow + i) =
-                        make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                }
-              }
-            } else {
-              bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
-  #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (col0 + i < p.N) {
-                  uint4 o;
-                  o.x = pack_bf16x2(f[i], f[i + 1]);
-                  o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                  o.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                  o.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                  *reinterpret_cast<uint4*>(crow + i) = o;
-                }
-              }
-            }
-          }
-        }
-        }
+        gemm_epilogue_store<BLOCK_N>(p, tmC, smem_c, taddr, warp, lane, m_blk, n_blk, split,
+                                     store_count);
       } else if constexpr (EPI == EPI_NCE_FWD) {
         // Per row and column block: running maximum m and sum of 2^(x - m), x = s*log2(e), with an
         // online rescale per 32-column chunk (no fixed shift: a fixed exp(s - alpha) underflows
@@ -507,6 +527,192 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 5) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =============================================================================================
+// CTA-pair variant (cta_group::2) of the EPI_STORE GEMM: one 256 x 256 output tile per 2-CTA
+// cluster.  CTA rank r stages rows [128 r, 128 r + 128) of the A tile and columns
+// [128 r, 128 r + 128) of the B tile (32 KiB per k-block instead of 48 KiB for a 128 x 256 tile of
+// its own), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both
+// CTAs' shared memory and writes each CTA's 128 accumulator rows into that CTA's TMEM.  With
+// K = 512..768 the single-CTA kernel is bound by L2 -> shared-memory operand traffic
+// (148 SMs x 48 KiB / 512 clk ~ the measured ~6.3 kB/clk TMA limit); the pair cuts it by a third.
+//
+// Barriers: full[stage] lives in the LEADER (its arrive.expect_tx covers the 64 KiB both CTAs
+// load; the peer's TMA credits the leader's barrier); empty[stage] and tmem_full[acc] are
+// multicast-committed into both CTAs; tmem_empty[acc] lives in the leader and counts the eight
+// epilogue warps of both CTAs.
+struct Gemm2Smem {
+  static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB: this CTA's 128 rows of A
+  static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kStagingBytes = 2 * 128 * 128;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
+};
+
+template <int A_MAJOR, int B_MAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using S = Gemm2Smem;
+  constexpr int kStages = S::kStages;
+  constexpr int BLOCK_N = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint8_t* smem_c = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + S::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  const int num_m2 = (p.M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM);
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_kb = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+  const int splits = p.split_k > 0 ? p.split_k : 1;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  const int num_tiles = num_m2 * num_n * splits;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && XCLIP_ONE_LANE(lane)) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.use_tma_store) tma_prefetch_desc(&tmC);
+  }
+  if (warp == 5) tmem_alloc_pair_512(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();             // barriers of BOTH CTAs are initialised before any remote arrive
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (XCLIP_ONE_LANE(lane)) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        const int tmn = t % (num_n * num_m2);
+        const int n_blk = tmn % num_n;
+        const int m_blk = (tmn / num_n) * 2 + (int)rank;
+        const int n0 = n_blk * BLOCK_N + (int)rank * 128;
+        const int split = t / (num_n * num_m2);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+          uint8_t* sa = smem_a + stage * S::kABytes;
+          uint8_t* sb = smem_b + stage * S::kBBytes;
+          if (A_MAJOR == kMajorK) {
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d_pair(sa + g * (kGemmBlockK * 128), &tmA, &full_bar[stage],
+                               m_blk * kGemmBlockM + g * 64, kb * kGemmBlockK);
+          }
+          if (B_MAJOR == kMajorK) {
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * kGemmBlockK, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d_pair(sb + g * (kGemmBlockK * 128), &tmB, &full_bar[stage], n0 + g * 64,
+                               kb * kGemmBlockK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
+      constexpr uint32_t kLboMN = kGemmBlockK * 128;
+      constexpr uint32_t kAStep = (A_MAJOR == kMajorK) ? 32u : 2048u;
+      constexpr uint32_t kBStep = (B_MAJOR == kMajorK) ? 32u : 2048u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += npairs, ++it) {
+        const int split = t / (num_n * num_m2);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (XCLIP_ONE_LANE(lane)) {
+            const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * S::kABytes),
+                                                  A_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
+            const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * S::kBBytes),
+                                                  B_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
+#pragma unroll
+            for (int k = 0; k < kGemmBlockK / 16; ++k)
+              umma_bf16_pair(tmem_d, desc_advance(adesc, k * kAStep), desc_advance(bdesc, k * kBStep),
+                             idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3, both CTAs) =====================
+    int it = 0;
+    uint32_t store_count = 0;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int tmn = t % (num_n * num_m2);
+      const int n_blk = tmn % num_n;
+      const int m_blk = (tmn / num_n) * 2 + (int)rank;
+      const int split = t / (num_n * num_m2);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BLOCK_N;
+      gemm_epilogue_store<BLOCK_N>(p, tmC, smem_c, taddr, warp, lane, m_blk, n_blk, split, store_count);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+    if (p.use_tma_store && threadIdx.x == 0)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();             // nobody exits (or frees TMEM) while the peer may still signal it
+  if (warp == 5) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair_512(tmem_base);
   }
 }
 
