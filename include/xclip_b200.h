@@ -186,6 +186,13 @@ int xclip_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos,
 int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float* dpos, float* dcls,
                          int B, int n, int d, int vocab, xclip_stream_t stream);
 
+/* ---- fused AdamW (the optimizer step behind the gradient all-reduce; the reference
+ * leaves optimisation to the user, README.md:44-58) over one flat f32 buffer; identical update rule to
+ * torch.optim.AdamW (decoupled decay, bias correction with `step` >= 1); g is read as g*grad_scale. */
+int xclip_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     xclip_stream_t stream);
+
 /* ---- rotary position embedding (x_clip/x_clip.py:155-176, applied to q, k and v at :221-223) ----
  * In place on the bf16 qkv buffer [rows, ld] (rows = B*n tokens, position = row %% n): in each of
  * the `nslices` consecutive 64-wide head slices the first 32 features are rotated pairwise

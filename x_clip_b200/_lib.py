@@ -61,6 +61,8 @@ SIGNATURES = {
                                      c_int, c_int, c_void_p]),
     "xclip_text_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_void_p]),
+    "xclip_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
+                                 c_float, c_float, c_int, c_float, c_void_p]),
     "xclip_rotary_inplace": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
                                      c_void_p]),
     "xclip_filip_segmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,

@@ -246,6 +246,17 @@ def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale, causal=False):
     return dqkv
 
 
+def adamw_step_(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """In-place fused AdamW over flat fp32 buffers (see xclip_adamw_step)."""
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _need(t, F32, nm)
+        if not t.is_contiguous() or t.numel() != p.numel():
+            raise _lib.XClipB200Error(f"adamw: {nm} must be contiguous with {p.numel()} elements")
+    _call(p, "adamw", 0.0, 28.0 * p.numel(), "xclip_adamw_step", p.data_ptr(), g.data_ptr(), m.data_ptr(),
+          v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+          int(step), float(grad_scale))
+
+
 def rotary_(qkv, n, nslices, cos_tab, sin_tab, inverse=False):
     """In-place rotary embedding of the q | k | v head slices (see xclip_rotary_inplace)."""
     _need(qkv, BF16, "qkv"); _rows2d(qkv, "qkv"); _need(cos_tab, F32, "cos"); _need(sin_tab, F32, "sin")
