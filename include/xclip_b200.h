@@ -186,6 +186,32 @@ int xclip_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos,
 int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float* dpos, float* dcls,
                          int B, int n, int d, int vocab, xclip_stream_t stream);
 
+/* ---- fused feed-forward block (x_clip/x_clip.py:180-199) on the CTA-pair GEMM ------------------
+ * FeedForward = Linear(d, 8d) -> GEGLU -> LayerNorm(4d) -> Linear(4d, d), + residual (:289).
+ *   ff_permute_cast : bf16 copy of net.0.weight [8d, d] with rows reordered so that a 256-row tile
+ *                     holds 128 value rows and the 128 MATCHING gate rows.
+ *   ff_scale_cast   : w2g = bf16(net.4.weight [d, 4d] * net.2.g [4d]) and colvec[j] = sum_k w2g[j,k].
+ *   ff_up           : u = [value | gate] bf16 [M, 8d] (reference layout, kept for the backward),
+ *                     hp = value * gelu_erf(gate) bf16 [M, 4d], rowsum[r] += (sum hp, sum hp^2)
+ *                     (rowsum f32 [M, 2], zeroed by the caller) - one GEMM, GEGLU in its epilogue.
+ *   ff_down         : out = rstd_r * (hp w2g^T - mean_r * colvec) + residual  (== LN(hp) g W2^T + x1),
+ *                     acc_out = bf16(hp w2g^T), stats[r] = (mean, rstd) - one GEMM.
+ *   ff_bwd_prep     : dxs = bf16(dx * rstd_r) [M, d]; vsum[j] += sum_r dxs[r,j] * mean_r.
+ *   ff_w2_grad_post : in place on raw = dxs^T hp (f32 [d, 4d]): dW2[j,k] = g[k] * (raw[j,k] - vsum[j]).
+ * d in 256*{1,2,3,4}; all matrices row-major, bf16 unless stated. */
+int xclip_ff_permute_cast(const float* w1, void* out, int d, xclip_stream_t stream);
+int xclip_ff_scale_cast(const float* w2, const float* g, void* w2g, float* colvec, int d,
+                        xclip_stream_t stream);
+int xclip_ff_up(const void* x, int64_t ldx, const void* w1p, void* u, int64_t ldu, void* hp,
+                int64_t ldhp, float* rowsum, int M, int d, xclip_stream_t stream);
+int xclip_ff_down(const void* hp, int64_t ldhp, const void* w2g, const float* colvec,
+                  const float* rowsum, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                  void* acc_out, int64_t ldacc, float* stats, float eps, int M, int d,
+                  xclip_stream_t stream);
+int xclip_ff_bwd_prep(const void* dx, int64_t lddx, const float* stats, void* dxs, float* vsum,
+                      int rows, int d, xclip_stream_t stream);
+int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float* g, int d, xclip_stream_t stream);
+
 /* ---- fused AdamW (the optimizer step behind the gradient all-reduce; the reference
  * leaves optimisation to the user, README.md:44-58) over one flat f32 buffer; identical update rule to
  * torch.optim.AdamW (decoupled decay, bias correction with `step` >= 1); g is read as g*grad_scale. */

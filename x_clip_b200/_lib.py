@@ -61,6 +61,14 @@ SIGNATURES = {
                                      c_int, c_int, c_void_p]),
     "xclip_text_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_void_p]),
+    "xclip_ff_permute_cast": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "xclip_ff_scale_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "xclip_ff_up": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                            c_int, c_int, c_void_p]),
+    "xclip_ff_down": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                              c_int64, c_void_p, c_int64, c_void_p, c_float, c_int, c_int, c_void_p]),
+    "xclip_ff_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "xclip_ff_w2_grad_post": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "xclip_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                  c_float, c_float, c_int, c_float, c_void_p]),
     "xclip_rotary_inplace": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,

@@ -1,5 +1,5 @@
 // C-ABI launcher for the tcgen05 GEMM (see gemm.cuh and include/xclip_b200.h).
-#include "gemm.cuh"
+#include "gemm_pair.cuh"
 #include "host.h"
 
 namespace xclip {
@@ -34,11 +34,12 @@ static int dispatch_major(int a_major, int b_major, const CUtensorMap& tmA, cons
 template <int A_MAJOR, int B_MAJOR>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                             const GemmParams& p, int pairs, cudaStream_t stream) {
-  auto kern = gemm2_bf16_kernel<A_MAJOR, B_MAJOR>;
-  const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Gemm2Smem::kTotal);
+  using S = PairCfg<PEPI_STORE>;
+  auto kern = gemm_pair_kernel<A_MAJOR, B_MAJOR, PEPI_STORE>;
+  const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), S::kTotal);
   if (rc_attr) return rc_attr;
-  kern<<<2 * pairs, kGemmThreads, Gemm2Smem::kTotal, stream>>>(tmA, tmB, tmC, p);   // __cluster_dims__(2,1,1)
-  XCLIP_LAUNCH_CHECK("gemm2_bf16_kernel");
+  kern<<<2 * pairs, S::kThreads, S::kTotal, stream>>>(tmA, tmB, tmC, tmC, p);   // __cluster_dims__(2,1,1)
+  XCLIP_LAUNCH_CHECK("gemm_pair_kernel");
   return XCLIP_OK;
 }
 

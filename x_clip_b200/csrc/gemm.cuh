@@ -57,6 +57,12 @@ struct GemmParams {
   const float* col_add;    // [N] or null: per-column addend (-FLT_MAX for masked text tokens)
   float* seg_max;          // [M, n_segs]  max_i s
   int* seg_arg;            // [M, n_segs]  argmax (index inside the segment)
+  // ---- fused feed-forward epilogues of the CTA-pair kernel (gemm_pair.cuh)
+  float* ff_rowsum;        // [M,2] (sum, sum of squares) of the GEGLU output rows: UP accumulates, DOWN reads
+  const float* ff_colvec;  // DOWN: c[N] = row sums of the gain-scaled down-projection weight
+  float* ff_stats;         // DOWN: [M,2] (mean, rstd) of the GEGLU output rows, written for the backward
+  float ff_eps;            // LayerNorm epsilon
+  int ff_hidden;           // 4*dim: LayerNorm width; column offset of the gate half inside u
 };
 
 constexpr int EPI_STORE = 0;    // C = alpha*acc (+bias) (+residual)
@@ -527,192 +533,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 5) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
-  }
-}
-
-// =============================================================================================
-// CTA-pair variant (cta_group::2) of the EPI_STORE GEMM: one 256 x 256 output tile per 2-CTA
-// cluster.  CTA rank r stages rows [128 r, 128 r + 128) of the A tile and columns
-// [128 r, 128 r + 128) of the B tile (32 KiB per k-block instead of 48 KiB for a 128 x 256 tile of
-// its own), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both
-// CTAs' shared memory and writes each CTA's 128 accumulator rows into that CTA's TMEM.  With
-// K = 512..768 the single-CTA kernel is bound by L2 -> shared-memory operand traffic
-// (148 SMs x 48 KiB / 512 clk ~ the measured ~6.3 kB/clk TMA limit); the pair cuts it by a third.
-//
-// Barriers: full[stage] lives in the LEADER (its arrive.expect_tx covers the 64 KiB both CTAs
-// load; the peer's TMA credits the leader's barrier); empty[stage] and tmem_full[acc] are
-// multicast-committed into both CTAs; tmem_empty[acc] lives in the leader and counts the eight
-// epilogue warps of both CTAs.
-struct Gemm2Smem {
-  static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB: this CTA's 128 rows of A
-  static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 6;
-  static constexpr int kStagingBytes = 2 * 128 * 128;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
-};
-
-template <int A_MAJOR, int B_MAJOR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using S = Gemm2Smem;
-  constexpr int kStages = S::kStages;
-  constexpr int BLOCK_N = 256;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint8_t* smem_c = smem + kStages * S::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + S::kStagingBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* tmem_full = bars + 2 * kStages;
-  uint64_t* tmem_empty = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1;
-  const int npairs = gridDim.x >> 1;
-
-  const int num_m2 = (p.M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM);
-  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_kb = (p.K + kGemmBlockK - 1) / kGemmBlockK;
-  const int splits = p.split_k > 0 ? p.split_k : 1;
-  const int kb_per_split = (num_kb + splits - 1) / splits;
-  const int num_tiles = num_m2 * num_n * splits;
-
-  if (threadIdx.x == 0) {
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 4 && XCLIP_ONE_LANE(lane)) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (p.use_tma_store) tma_prefetch_desc(&tmC);
-  }
-  if (warp == 5) tmem_alloc_pair_512(tmem_slot);
-  tcgen05_fence_before();
-  cluster_sync_all();             // barriers of BOTH CTAs are initialised before any remote arrive
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 4) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (XCLIP_ONE_LANE(lane)) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += npairs) {
-        const int tmn = t % (num_n * num_m2);
-        const int n_blk = tmn % num_n;
-        const int m_blk = (tmn / num_n) * 2 + (int)rank;
-        const int n0 = n_blk * BLOCK_N + (int)rank * 128;
-        const int split = t / (num_n * num_m2);
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(kb0 + kb_per_split, num_kb);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-          uint8_t* sa = smem_a + stage * S::kABytes;
-          uint8_t* sb = smem_b + stage * S::kBBytes;
-          if (A_MAJOR == kMajorK) {
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM);
-          } else {
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-              tma_load_2d_pair(sa + g * (kGemmBlockK * 128), &tmA, &full_bar[stage],
-                               m_blk * kGemmBlockM + g * 64, kb * kGemmBlockK);
-          }
-          if (B_MAJOR == kMajorK) {
-            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * kGemmBlockK, n0);
-          } else {
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-              tma_load_2d_pair(sb + g * (kGemmBlockK * 128), &tmB, &full_bar[stage], n0 + g * 64,
-                               kb * kGemmBlockK);
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 5) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
-      constexpr uint32_t kLboMN = kGemmBlockK * 128;
-      constexpr uint32_t kAStep = (A_MAJOR == kMajorK) ? 32u : 2048u;
-      constexpr uint32_t kBStep = (B_MAJOR == kMajorK) ? 32u : 2048u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = pair; t < num_tiles; t += npairs, ++it) {
-        const int split = t / (num_n * num_m2);
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(kb0 + kb_per_split, num_kb);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          if (XCLIP_ONE_LANE(lane)) {
-            const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * S::kABytes),
-                                                  A_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
-            const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * S::kBBytes),
-                                                  B_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
-#pragma unroll
-            for (int k = 0; k < kGemmBlockK / 16; ++k)
-              umma_bf16_pair(tmem_d, desc_advance(adesc, k * kAStep), desc_advance(bdesc, k * kBStep),
-                             idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_commit_pair(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
-          }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 0-3, both CTAs) =====================
-    int it = 0;
-    uint32_t store_count = 0;
-    for (int t = pair; t < num_tiles; t += npairs, ++it) {
-      const int tmn = t % (num_n * num_m2);
-      const int n_blk = tmn % num_n;
-      const int m_blk = (tmn / num_n) * 2 + (int)rank;
-      const int split = t / (num_n * num_m2);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BLOCK_N;
-      gemm_epilogue_store<BLOCK_N>(p, tmC, smem_c, taddr, warp, lane, m_blk, n_blk, split, store_count);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-    }
-    if (p.use_tma_store && threadIdx.x == 0)
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-
-  tcgen05_fence_before();
-  cluster_sync_all();             // nobody exits (or frees TMEM) while the peer may still signal it
-  if (warp == 5) {
-    tcgen05_fence_after();
-    tmem_dealloc_pair_512(tmem_base);
   }
 }
 

@@ -1,0 +1,347 @@
+// CTA-pair (cta_group::2) tcgen05 GEMM: one 256 x 256 output tile per 2-CTA cluster.
+//
+// CTA rank r stages rows [128 r, 128 r + 128) of the A tile and columns [128 r, 128 r + 128) of the
+// B tile (32 KiB per k-block instead of 48 KiB for a 128 x 256 tile of its own); the leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads both CTAs' shared memory and
+// writes each CTA's 128 accumulator rows into that CTA's TMEM.  With K = 512..768 the single-CTA
+// kernel (gemm.cuh) is bound by L2 -> shared-memory operand traffic; the pair cuts it by a third
+// (measured on a B200: 1176 -> 1373 TFLOP/s for [50176 x 768] x [2304 x 768]^T).
+//
+// Barriers: full[stage] lives in the LEADER (its arrive.expect_tx covers the 64 KiB both CTAs
+// load; the peer's TMA credits the leader's barrier); empty[stage] and tmem_full[acc] are
+// multicast-committed into both CTAs; tmem_empty[acc] lives in the leader and counts the
+// epilogue warps of both CTAs.
+//
+// Epilogues (template parameter EPI):
+//   PEPI_STORE   C = alpha*acc (+bias) (+residual): bf16 via TMA stores / fp32 / fp32 atomic
+//   PEPI_FF_UP   feed-forward up-projection with GEGLU fused (x_clip/x_clip.py:180-183,191-192):
+//                B is the up-projection weight with its rows permuted so that a tile holds the
+//                value columns [128 t, 128 t + 128) and the MATCHING gate columns; writes
+//                u = [value | gate] (reference layout, needed by the backward), hp = value *
+//                gelu(gate) (bf16) and accumulates per-row (sum, sum^2) of bf16(hp).
+//   PEPI_FF_DOWN feed-forward down-projection with the LayerNorm folded in (:193-195):
+//                x2 = LN(hp) g W2^T + x1 = rstd_r (acc_rj - mean_r c_j) + x1_rj  with
+//                acc = hp (W2 . g)^T and c_j = sum_k (W2 . g)_jk; also writes bf16(acc) and
+//                (mean, rstd) for the backward.
+#pragma once
+
+#include "gemm.cuh"
+
+namespace xclip {
+
+constexpr int PEPI_STORE = 0;
+constexpr int PEPI_FF_UP = 1;
+constexpr int PEPI_FF_DOWN = 2;
+
+template <int EPI>
+struct PairCfg {
+  static constexpr int kEpiWarps = EPI == PEPI_FF_UP ? 8 : 4;
+  static constexpr int kThreads = (kEpiWarps + 2) * 32;
+  static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB: this CTA's 128 rows of A
+  static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBox = 128 * 128;                          // one [128 rows x 64 bf16] staging box
+  // STORE: 2 boxes (double buffered); FF_UP: (value, gate, hp) x 2 column halves; FF_DOWN: (out, acc)
+  static constexpr int kStagingBytes = (EPI == PEPI_FF_UP ? 6 : 2) * kBox;
+  static constexpr int kStages = EPI == PEPI_FF_UP ? 4 : 6;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void st_box_bf16x8(uint32_t box, int row, int chunk, const float* f) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + swz128(row, chunk)),
+               "r"(pack_bf16x2(f[0], f[1])), "r"(pack_bf16x2(f[2], f[3])),
+               "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+               : "memory");
+}
+__device__ __forceinline__ float bf16_rn(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <int A_MAJOR, int B_MAJOR, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI>::kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                 const GemmParams p) {
+  using S = PairCfg<EPI>;
+  constexpr int kStages = S::kStages;
+  constexpr int kEpiWarps = S::kEpiWarps;
+  constexpr int BLOCK_N = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint8_t* smem_c = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + S::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  const int num_m2 = (p.M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM);
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_kb = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+  const int splits = p.split_k > 0 ? p.split_k : 1;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  const int num_tiles = num_m2 * num_n * splits;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps && XCLIP_ONE_LANE(lane)) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI != PEPI_STORE || p.use_tma_store) tma_prefetch_desc(&tmC);
+    if (EPI != PEPI_STORE) tma_prefetch_desc(&tmC2);
+  }
+  if (warp == kEpiWarps + 1) tmem_alloc_pair_512(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();             // barriers of BOTH CTAs are initialised before any remote arrive
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpiWarps) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (XCLIP_ONE_LANE(lane)) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        const int tmn = t % (num_n * num_m2);
+        const int n_blk = tmn % num_n;
+        const int m_blk = (tmn / num_n) * 2 + (int)rank;
+        const int n0 = n_blk * BLOCK_N + (int)rank * 128;
+        const int split = t / (num_n * num_m2);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+          uint8_t* sa = smem_a + stage * S::kABytes;
+          uint8_t* sb = smem_b + stage * S::kBBytes;
+          if (A_MAJOR == kMajorK) {
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d_pair(sa + g * (kGemmBlockK * 128), &tmA, &full_bar[stage],
+                               m_blk * kGemmBlockM + g * 64, kb * kGemmBlockK);
+          }
+          if (B_MAJOR == kMajorK) {
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * kGemmBlockK, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d_pair(sb + g * (kGemmBlockK * 128), &tmB, &full_bar[stage], n0 + g * 64,
+                               kb * kGemmBlockK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
+      constexpr uint32_t kLboMN = kGemmBlockK * 128;
+      constexpr uint32_t kAStep = (A_MAJOR == kMajorK) ? 32u : 2048u;
+      constexpr uint32_t kBStep = (B_MAJOR == kMajorK) ? 32u : 2048u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += npairs, ++it) {
+        const int split = t / (num_n * num_m2);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (XCLIP_ONE_LANE(lane)) {
+            const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * S::kABytes),
+                                                  A_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
+            const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * S::kBBytes),
+                                                  B_MAJOR == kMajorK ? 0u : kLboMN, 1024u);
+#pragma unroll
+            for (int k = 0; k < kGemmBlockK / 16; ++k)
+              umma_bf16_pair(tmem_d, desc_advance(adesc, k * kAStep), desc_advance(bdesc, k * kBStep),
+                             idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0..kEpiWarps-1, both CTAs) =====================
+    int it = 0;
+    uint32_t store_count = 0;
+    const int quarter = warp & 3;                 // TMEM lane quarter
+    const int half = warp >> 2;                   // FF_UP: which 64 hidden columns of the tile
+    const int row_in_tile = quarter * 32 + lane;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int tmn = t % (num_n * num_m2);
+      const int n_blk = tmn % num_n;
+      const int m_blk = (tmn / num_n) * 2 + (int)rank;
+      const int split = t / (num_n * num_m2);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const int row = m_blk * kGemmBlockM + row_in_tile;
+      const bool row_ok = row < p.M;
+      if constexpr (EPI == PEPI_STORE) {
+        gemm_epilogue_store<BLOCK_N>(p, tmC, smem_c, taddr, warp, lane, m_blk, n_blk, split, store_count);
+      } else if constexpr (EPI == PEPI_FF_UP) {
+        // accumulator columns [0,128) = value, [128,256) = gate of hidden units [128 n_blk, +128)
+        const uint32_t stg = smem_u32(smem_c) + half * 3 * S::kBox;   // value | gate | hp boxes
+        const bool issuer = (threadIdx.x == half * 128);
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          uint32_t vv[32], gg[32];
+          tmem_ld_32x32(taddr + half * 64 + c32 * 32, vv);
+          tmem_ld_32x32(taddr + 128 + half * 64 + c32 * 32, gg);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float va[8], ga[8], hp[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              va[e] = __uint_as_float(vv[i + e]);
+              ga[e] = __uint_as_float(gg[i + e]);
+              hp[e] = bf16_rn(va[e] * gelu_erf(ga[e]));   // statistics of what the next GEMM reads
+              s1 += hp[e];
+              s2 = fmaf(hp[e], hp[e], s2);
+            }
+            const int chunk = c32 * 4 + (i >> 3);
+            st_box_bf16x8(stg, row_in_tile, chunk, va);
+            st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, ga);
+            st_box_bf16x8(stg + 2 * S::kBox, row_in_tile, chunk, hp);
+          }
+        }
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        if (issuer) {
+          const int hcol = n_blk * 128 + half * 64;            // hidden-unit column of this box
+          const int r0 = m_blk * kGemmBlockM;
+          tma_store_2d(&tmC, stg, hcol, r0);                    // u[:, hcol ..]            value
+          tma_store_2d(&tmC, stg + S::kBox, p.ff_hidden + hcol, r0);   // u[:, 4d + hcol ..]  gate
+          tma_store_2d(&tmC2, stg + 2 * S::kBox, hcol, r0);     // hp[:, hcol ..]
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (row_ok) {
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row), "f"(s1) : "memory");
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row + 1), "f"(s2) : "memory");
+        }
+      } else {   // PEPI_FF_DOWN
+        const uint32_t stg = smem_u32(smem_c);                  // out box | acc box
+        const float invD = 1.f / (float)p.ff_hidden;
+        float mean = 0.f, rstd = 0.f;
+        if (row_ok) {
+          const float2 ss = *reinterpret_cast<const float2*>(p.ff_rowsum + 2ll * row);
+          mean = ss.x * invD;
+          rstd = rsqrtf(fmaxf(ss.y * invD - mean * mean, 0.f) + p.ff_eps);
+          if (n_blk == 0) *reinterpret_cast<float2*>(p.ff_stats + 2ll * row) = make_float2(mean, rstd);
+        }
+        const bf16* res_row = (p.residual != nullptr && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;
+#pragma unroll 1
+        for (int q = 0; q < BLOCK_N / 64; ++q) {
+          if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int c32 = 0; c32 < 2; ++c32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + q * 64 + c32 * 32, v);
+            tmem_ld_wait();
+            const int col0 = n_blk * BLOCK_N + q * 64 + c32 * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float a8[8], o8[8];
+              float r8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              if (res_row != nullptr && col0 + i < p.N) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + col0 + i);
+                float2 x0 = unpack_bf16x2(r4.x), x1 = unpack_bf16x2(r4.y);
+                float2 x2 = unpack_bf16x2(r4.z), x3 = unpack_bf16x2(r4.w);
+                r8[0] = x0.x; r8[1] = x0.y; r8[2] = x1.x; r8[3] = x1.y;
+                r8[4] = x2.x; r8[5] = x2.y; r8[6] = x3.x; r8[7] = x3.y;
+              }
+              float c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              if (col0 + i < p.N) {
+                const float4 c0 = *reinterpret_cast<const float4*>(p.ff_colvec + col0 + i);
+                const float4 c1 = *reinterpret_cast<const float4*>(p.ff_colvec + col0 + i + 4);
+                c8[0] = c0.x; c8[1] = c0.y; c8[2] = c0.z; c8[3] = c0.w;
+                c8[4] = c1.x; c8[5] = c1.y; c8[6] = c1.z; c8[7] = c1.w;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                a8[e] = __uint_as_float(v[i + e]);
+                o8[e] = fmaf(rstd, a8[e] - mean * c8[e], r8[e]);
+              }
+              const int chunk = c32 * 4 + (i >> 3);
+              st_box_bf16x8(stg, row_in_tile, chunk, o8);
+              st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, a8);
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 0) {
+            const int c0 = n_blk * BLOCK_N + q * 64;
+            if (c0 < p.N) {
+              tma_store_2d(&tmC, stg, c0, m_blk * kGemmBlockM);
+              tma_store_2d(&tmC2, stg + S::kBox, c0, m_blk * kGemmBlockM);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+    // outstanding TMA stores must have READ their staging smem before the CTA exits
+    if (EPI == PEPI_FF_UP) {
+      if ((threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if ((EPI != PEPI_STORE || p.use_tma_store) && threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();             // nobody exits (or frees TMEM) while the peer may still signal it
+  if (warp == kEpiWarps + 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair_512(tmem_base);
+  }
+}
+
+}  // namespace xclip

@@ -23,7 +23,25 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 LN_EPS = 1e-5   # the reference's fp32 branch (x_clip.py:118); parameters/outputs are fp32-facing
 
+# Fused feed-forward (csrc/ff.cu): GEGLU in the up-projection's epilogue, LayerNorm(4d) folded into
+# the down-projection.  False selects the separate geglu_ln_fwd kernel (kept for A/B measurements).
+FUSED_FF = True
+
 _scope_cache = None     # dict while a weight_scope() is active, else None
+
+
+def ff_weights(w1: torch.Tensor, w2: torch.Tensor, g4: torch.Tensor):
+    """(w1 permuted bf16, w2*g4 bf16, row sums) for the fused feed-forward; shared inside a
+    weight_scope() like weight_bf16."""
+    key = ("ff", id(w1), id(w2), id(g4))
+    if _scope_cache is not None:
+        hit = _scope_cache.get(key)
+        if hit is not None and hit[0] is w1:
+            return hit[1]
+    out = K.ff_weights(w1.detach(), w2.detach(), g4.detach())
+    if _scope_cache is not None:
+        _scope_cache[key] = (w1, out)
+    return out
 
 
 def weight_bf16(p: torch.Tensor) -> torch.Tensor:
@@ -141,9 +159,16 @@ class TransformerFn(torch.autograd.Function):
             y = K.gemm(o, bo)
             # x1 = LN(y)*go + x ; xn2 = LN(x1)*g2   (attention tail + feed-forward pre-norm)
             x1, st_y, xn2, st_x1 = K.layernorm_fwd(y, go, res=xcur, g2=g2, eps=LN_EPS)
-            u = K.gemm(xn2, b1)
-            h, st_v = K.geglu_ln_fwd(u, g4, eps=LN_EPS)
-            x2 = K.gemm(h, b2, residual=x1)
+            if FUSED_FF:
+                # h below is hp = value*gelu(gate) BEFORE the LayerNorm (the norm is folded into
+                # the down-projection); the backward knows from ctx.fused_ff
+                w1p, w2g, colvec = ff_weights(w1, w2, g4)
+                u, h, rowsum = K.ff_up(xn2, w1p)
+                x2, _acc, st_v = K.ff_down(h, w2g, colvec, rowsum, x1, LN_EPS)
+            else:
+                u = K.gemm(xn2, b1)
+                h, st_v = K.geglu_ln_fwd(u, g4, eps=LN_EPS)
+                x2 = K.gemm(h, b2, residual=x1)
             saved.append((xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h))
             xcur = x2
             if L + 1 < depth:
@@ -155,6 +180,7 @@ class TransformerFn(torch.autograd.Function):
         ctx.mask = mask_c
         ctx.dims = (B, n, d, heads, depth, scale, causal)
         ctx.rot = (rot_cos, rot_sin)
+        ctx.fused_ff = FUSED_FF
         ctx.weights = weights
         ctx.wb = wb
         return out.view(B, n, d)
@@ -187,7 +213,12 @@ class TransformerFn(torch.autograd.Function):
             base = 2 + 8 * L
             # feed-forward: x2 = h @ w2^T + x1
             dh = K.gemm(dx, b2, b_major=1)
-            grads[base + 7] = wg.wgrad(dx, h)
+            if ctx.fused_ff:
+                # h is the pre-norm hp: dW2 = g4 * (dxs^T hp - vsum (x) 1), dxs = dx * rstd
+                dxs, vsum = K.ff_bwd_prep(dx, st_v)
+                grads[base + 7] = K.ff_w2_grad_post_(wg.wgrad(dxs, h), vsum, g4.detach())
+            else:
+                grads[base + 7] = wg.wgrad(dx, h)
             dg4 = torch.zeros(g4.shape[0], device=dev, dtype=F32)
             du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
             grads[base + 6] = dg4

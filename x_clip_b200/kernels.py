@@ -246,6 +246,70 @@ def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale, causal=False):
     return dqkv
 
 
+def ff_weights(w1, w2, g4):
+    """bf16 operands of the fused feed-forward: row-permuted up-projection, gain-scaled
+    down-projection and its row sums (see xclip_ff_permute_cast / xclip_ff_scale_cast)."""
+    _need(w1, F32, "w1"); _need(w2, F32, "w2"); _need(g4, F32, "g4")
+    d = w1.shape[1]
+    if tuple(w1.shape) != (8 * d, d) or tuple(w2.shape) != (d, 4 * d) or g4.numel() != 4 * d:
+        raise _lib.XClipB200Error("ff_weights: shapes must be [8d,d], [d,4d], [4d]")
+    w1, w2, g4 = w1.contiguous(), w2.contiguous(), g4.contiguous()
+    w1p = torch.empty((8 * d, d), device=w1.device, dtype=BF16)
+    w2g = torch.empty((d, 4 * d), device=w1.device, dtype=BF16)
+    colvec = torch.empty((d,), device=w1.device, dtype=F32)
+    _call(w1, "cast", 0.0, 6.0 * w1.numel(), "xclip_ff_permute_cast", w1.data_ptr(), w1p.data_ptr(), d)
+    _call(w2, "cast", 0.0, 6.0 * w2.numel(), "xclip_ff_scale_cast", w2.data_ptr(), g4.data_ptr(),
+          w2g.data_ptr(), colvec.data_ptr(), d)
+    return w1p, w2g, colvec
+
+
+def ff_up(x, w1p):
+    """x bf16 [M,d] -> (u bf16 [M,8d] = [value|gate], hp bf16 [M,4d], rowsum f32 [M,2])."""
+    _need(x, BF16, "x"); _rows2d(x, "x"); _need(w1p, BF16, "w1p")
+    M, d = x.shape
+    u = torch.empty((M, 8 * d), device=x.device, dtype=BF16)
+    hp = torch.empty((M, 4 * d), device=x.device, dtype=BF16)
+    rowsum = torch.zeros((M, 2), device=x.device, dtype=F32)
+    _call(x, "gemm_fwd", 2.0 * M * 8 * d * d, 2.0 * (M * d + 8 * d * d + M * 12 * d), "xclip_ff_up",
+          x.data_ptr(), x.stride(0), w1p.data_ptr(), u.data_ptr(), u.stride(0), hp.data_ptr(),
+          hp.stride(0), rowsum.data_ptr(), M, d)
+    return u, hp, rowsum
+
+
+def ff_down(hp, w2g, colvec, rowsum, res, eps):
+    """(x2 bf16 [M,d] = LN(hp) g W2^T + res, acc bf16 [M,d], stats f32 [M,2])."""
+    _need(hp, BF16, "hp"); _rows2d(hp, "hp"); _need(w2g, BF16, "w2g"); _need(res, BF16, "res"); _rows2d(res, "res")
+    M = hp.shape[0]
+    d = w2g.shape[0]
+    out = torch.empty((M, d), device=hp.device, dtype=BF16)
+    acc = torch.empty((M, d), device=hp.device, dtype=BF16)
+    stats = torch.empty((M, 2), device=hp.device, dtype=F32)
+    _call(hp, "gemm_fwd", 2.0 * M * d * 4 * d, 2.0 * (M * 4 * d + 4 * d * d + 3 * M * d), "xclip_ff_down",
+          hp.data_ptr(), hp.stride(0), w2g.data_ptr(), colvec.data_ptr(), rowsum.data_ptr(),
+          res.data_ptr(), res.stride(0), out.data_ptr(), out.stride(0), acc.data_ptr(), acc.stride(0),
+          stats.data_ptr(), float(eps), M, d)
+    return out, acc, stats
+
+
+def ff_bwd_prep(dx, stats):
+    """-> (dxs bf16 [M,d] = dx * rstd, vsum f32 [d] = sum_r dxs[r] * mean_r)."""
+    _need(dx, BF16, "dx"); _rows2d(dx, "dx"); _need(stats, F32, "stats")
+    M, d = dx.shape
+    dxs = torch.empty((M, d), device=dx.device, dtype=BF16)
+    vsum = torch.zeros((d,), device=dx.device, dtype=F32)
+    _call(dx, "ff_small", 0.0, 4.0 * M * d, "xclip_ff_bwd_prep", dx.data_ptr(), dx.stride(0),
+          stats.data_ptr(), dxs.data_ptr(), vsum.data_ptr(), M, d)
+    return dxs, vsum
+
+
+def ff_w2_grad_post_(raw, vsum, g4):
+    _need(raw, F32, "raw"); _need(vsum, F32, "vsum"); _need(g4, F32, "g4")
+    d = raw.shape[0]
+    _call(raw, "ff_small", 0.0, 8.0 * raw.numel(), "xclip_ff_w2_grad_post", raw.data_ptr(), vsum.data_ptr(),
+          g4.data_ptr(), d)
+    return raw
+
+
 def adamw_step_(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     """In-place fused AdamW over flat fp32 buffers (see xclip_adamw_step)."""
     for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
