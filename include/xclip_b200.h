@@ -196,8 +196,13 @@ int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float*
  *                     (rowsum f32 [M, 2], zeroed by the caller) - one GEMM, GEGLU in its epilogue.
  *   ff_down         : out = rstd_r * (hp w2g^T - mean_r * colvec) + residual  (== LN(hp) g W2^T + x1),
  *                     acc_out = bf16(hp w2g^T), stats[r] = (mean, rstd) - one GEMM.
- *   ff_bwd_prep     : dxs = bf16(dx * rstd_r) [M, d]; vsum[j] += sum_r dxs[r,j] * mean_r.
- *   ff_w2_grad_post : in place on raw = dxs^T hp (f32 [d, 4d]): dW2[j,k] = g[k] * (raw[j,k] - vsum[j]).
+ *   ff_bwd_prep     : dxs = bf16(dx * rstd_r) [M, d]; vsum[j] += sum_r dxs[r,j] * mean_r; with acc and
+ *                     colvec also ab[r] = (mean_k gdh, mean_k gdh*hn) - the two row means of the
+ *                     LayerNorm backward, from d-wide data only (gdh = dx w2g is never formed here).
+ *   ff_bwd          : du [M, 8d] = backward of LayerNorm(4d) + GEGLU fused into the dgrad GEMM
+ *                     gdh = dx w2g (reads u, stats, ab; the [M, 4d] gradient never exists in HBM).
+ *   ff_w2_grad_post : in place on raw = dxs^T hp (f32 [d, 4d]): dW2[j,k] = g[k] * (raw[j,k] - vsum[j]);
+ *                     with w2/dg also dg[k] += sum_j (raw[j,k] - vsum[j]) * w2[j,k] (gain gradient).
  * d in 256*{1,2,3,4}; all matrices row-major, bf16 unless stated. */
 int xclip_ff_permute_cast(const float* w1, void* out, int d, xclip_stream_t stream);
 int xclip_ff_scale_cast(const float* w2, const float* g, void* w2g, float* colvec, int d,
@@ -208,9 +213,14 @@ int xclip_ff_down(const void* hp, int64_t ldhp, const void* w2g, const float* co
                   const float* rowsum, const void* residual, int64_t ldr, void* out, int64_t ldo,
                   void* acc_out, int64_t ldacc, float* stats, float eps, int M, int d,
                   xclip_stream_t stream);
-int xclip_ff_bwd_prep(const void* dx, int64_t lddx, const float* stats, void* dxs, float* vsum,
-                      int rows, int d, xclip_stream_t stream);
-int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float* g, int d, xclip_stream_t stream);
+int xclip_ff_bwd_prep(const void* dx, int64_t lddx, const float* stats, const void* acc, int64_t ldacc,
+                      const float* colvec, void* dxs, float* vsum, float* ab, int rows, int d,
+                      xclip_stream_t stream);
+int xclip_ff_bwd(const void* dx, int64_t lddx, const void* w2g, const void* u, int64_t ldu,
+                 const float* stats, const float* ab, void* du, int64_t lddu, int M, int d,
+                 xclip_stream_t stream);
+int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float* g, const float* w2, float* dg,
+                          int d, xclip_stream_t stream);
 
 /* ---- fused AdamW (the optimizer step behind the gradient all-reduce; the reference
  * leaves optimisation to the user, README.md:44-58) over one flat f32 buffer; identical update rule to

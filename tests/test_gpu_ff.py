@@ -43,13 +43,21 @@ def test_ff_forward_and_w2_gradient(cuda_device, M, d):
     rel = (x2.float() - x2_ref).norm().item() / x2_ref.norm().item()
     assert rel <= 5e-3, rel
 
-    # backward pieces: dW2 = dx^T LN(hp) g  without materialising LN(hp)
+    # backward: autograd over the fp32 restatement, on the bf16 activations the kernels saved
     dx = torch.randn(M, d, generator=g).to(dev).bfloat16()
-    dxs, vsum = K.ff_bwd_prep(dx, stats)
+    u_leaf = u.float().requires_grad_(True)
+    w2_leaf = w2.clone().requires_grad_(True)
+    g4_leaf = g4.clone().requires_grad_(True)
+    hp_a = u_leaf[:, :4 * d] * torch.nn.functional.gelu(u_leaf[:, 4 * d:])
+    (_ln(hp_a, g4_leaf) @ w2_leaf.t()).backward(dx.float())
+
+    dxs, vsum, ab = K.ff_bwd_prep(dx, stats, acc, colvec)
+    du = K.ff_bwd(dx, w2g, u, stats, ab)
     raw = torch.zeros(d, 4 * d, device=dev)
     K.gemm(dxs, hp, a_major=1, b_major=1, out=raw, accumulate=True)
-    dw2 = K.ff_w2_grad_post_(raw, vsum, g4)
+    dg4 = torch.zeros(4 * d, device=dev)
+    dw2 = K.ff_w2_grad_post_(raw, vsum, g4, w2, dg4)
     torch.cuda.synchronize()
-    dw2_ref = dx.float().t() @ _ln(hp.float(), g4)
-    rel = (dw2 - dw2_ref).norm().item() / dw2_ref.norm().item()
-    assert rel <= 1e-2, rel
+    for name, got, ref in (("du", du.float(), u_leaf.grad), ("dW2", dw2, w2_leaf.grad), ("dg4", dg4, g4_leaf.grad)):
+        rel = (got - ref).norm().item() / ref.norm().item()
+        assert rel <= 1.5e-2, (name, rel)

@@ -67,8 +67,11 @@ SIGNATURES = {
                             c_int, c_int, c_void_p]),
     "xclip_ff_down": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                               c_int64, c_void_p, c_int64, c_void_p, c_float, c_int, c_int, c_void_p]),
-    "xclip_ff_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "xclip_ff_w2_grad_post": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "xclip_ff_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p]),
+    "xclip_ff_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                             c_int64, c_int, c_int, c_void_p]),
+    "xclip_ff_w2_grad_post": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "xclip_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                  c_float, c_float, c_int, c_float, c_void_p]),
     "xclip_rotary_inplace": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,

@@ -68,64 +68,11 @@ ff_scale_cast_kernel(const float* __restrict__ w2, const float* __restrict__ g, 
   }
 }
 
-// dxs = bf16(dx * rstd_r);  vsum[j] += sum_r float(dxs[r,j]) * mean_r.   One warp per row.
-__global__ void __launch_bounds__(256)
-ff_bwd_prep_kernel(const bf16* __restrict__ dx, long long lddx, const float* __restrict__ stats,
-                   bf16* __restrict__ dxs, float* __restrict__ vsum, int rows, int d) {
-  extern __shared__ float acc_sm[];          // [d] block-level column partials
-  for (int i = threadIdx.x; i < d; i += blockDim.x) acc_sm[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int warp_stride = gridDim.x * (blockDim.x >> 5);
-  for (int row = warp_global; row < rows; row += warp_stride) {
-    const float mean = stats[2ll * row], rstd = stats[2ll * row + 1];
-    for (int c = lane * 8; c < d; c += 256) {
-      const uint4 r4 = *reinterpret_cast<const uint4*>(dx + row * lddx + c);
-      const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
-      float f[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 x = unpack_bf16x2(w[k]);
-        f[2 * k] = bf16_rn(x.x * rstd);
-        f[2 * k + 1] = bf16_rn(x.y * rstd);
-      }
-      uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(dxs + (long long)row * d + c) = o;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&acc_sm[c + e], f[e] * mean);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) atomicAdd(vsum + i, acc_sm[i]);
-}
-
-// in place: raw[j,k] <- g[k] * (raw[j,k] - vsum[j])
-__global__ void __launch_bounds__(256)
-ff_w2_grad_post_kernel(float* __restrict__ raw, const float* __restrict__ vsum,
-                       const float* __restrict__ g, int d) {
-  const long long D = 4ll * d;
-  const long long total = (long long)d * D / 4;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long e0 = idx * 4;
-    const long long j = e0 / D;
-    const long long k = e0 - j * D;
-    float4 r = *reinterpret_cast<float4*>(raw + e0);
-    const float4 gg = *reinterpret_cast<const float4*>(g + k);
-    const float v = vsum[j];
-    r.x = gg.x * (r.x - v); r.y = gg.y * (r.y - v); r.z = gg.z * (r.z - v); r.w = gg.w * (r.w - v);
-    *reinterpret_cast<float4*>(raw + e0) = r;
-  }
-}
-
-template <int EPI>
+template <int EPI, int B_MAJOR = kMajorK>
 static int launch_pair_ff(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t stream) {
   using S = PairCfg<EPI>;
-  auto kern = gemm_pair_kernel<kMajorK, kMajorK, EPI>;
+  auto kern = gemm_pair_kernel<kMajorK, B_MAJOR, EPI>;
   const int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), S::kTotal);
   if (rc) return rc;
   const long long tiles = (long long)((p.M + 255) / 256) * ((p.N + 255) / 256);
@@ -212,28 +159,24 @@ extern "C" int xclip_ff_down(const void* hp, int64_t ldhp, const void* w2g, cons
   return launch_pair_ff<PEPI_FF_DOWN>(tmA, tmB, tmC, tmC2, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int xclip_ff_bwd_prep(const void* dx, int64_t lddx, const float* stats, void* dxs,
-                                 float* vsum, int rows, int d, xclip_stream_t stream) {
+extern "C" int xclip_ff_bwd(const void* dx, int64_t lddx, const void* w2g, const void* u, int64_t ldu,
+                            const float* stats, const float* ab, void* du, int64_t lddu, int M, int d,
+                            xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
-  XCLIP_REQUIRE(dx && stats && dxs && vsum && rows > 0 && d > 0 && d % 256 == 0 && d <= 1024,
-                "ff_bwd_prep: bad arguments (d=%d)", d);
-  XCLIP_REQUIRE(lddx % 8 == 0 && lddx >= d && FF_ALIGNED(dx) && FF_ALIGNED(dxs), "ff_bwd_prep: misaligned");
-  int blocks = (rows + 7) / 8;
-  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-  ff_bwd_prep_kernel<<<blocks, 256, d * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dx), lddx, stats, reinterpret_cast<bf16*>(dxs), vsum, rows, d);
-  XCLIP_LAUNCH_CHECK("ff_bwd_prep_kernel");
-  return XCLIP_OK;
-}
-
-extern "C" int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float* g, int d,
-                                     xclip_stream_t stream) {
-  int rc = xclip_init();
-  if (rc) return rc;
-  XCLIP_REQUIRE(raw && vsum && g && d > 0 && d % 256 == 0, "ff_w2_grad_post: bad arguments");
-  XCLIP_REQUIRE(FF_ALIGNED(raw) && FF_ALIGNED(g), "ff_w2_grad_post: misaligned");
-  ff_w2_grad_post_kernel<<<num_sms() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(raw, vsum, g, d);
-  XCLIP_LAUNCH_CHECK("ff_w2_grad_post_kernel");
-  return XCLIP_OK;
+  XCLIP_REQUIRE(dx && w2g && u && stats && ab && du, "ff_bwd: null pointer");
+  XCLIP_REQUIRE(M > 0 && d > 0 && d % 256 == 0, "ff_bwd: M=%d d=%d (d %% 256)", M, d);
+  XCLIP_REQUIRE(lddx % 8 == 0 && lddx >= d && ldu % 8 == 0 && ldu >= 8 * d && lddu % 8 == 0 && lddu >= 8 * d,
+                "ff_bwd: bad leading dimensions");
+  XCLIP_REQUIRE(FF_ALIGNED(dx) && FF_ALIGNED(w2g) && FF_ALIGNED(u) && FF_ALIGNED(du), "ff_bwd: misaligned pointer");
+  CUtensorMap tmA, tmB, tmC;
+  if ((rc = encode_2d_bf16(&tmA, dx, (uint64_t)d, (uint64_t)M, (uint64_t)lddx, 64, kGemmBlockM))) return rc;
+  // B = w2g [d, 4d] consumed MN-major: contraction index d on rows, 64 x 64 boxes
+  if ((rc = encode_2d_bf16(&tmB, w2g, (uint64_t)(4 * d), (uint64_t)d, (uint64_t)(4 * d), 64, kGemmBlockK))) return rc;
+  if ((rc = encode_2d_bf16(&tmC, du, (uint64_t)(8 * d), (uint64_t)M, (uint64_t)lddu, 64, kGemmBlockM))) return rc;
+  GemmParams p = {};
+  p.M = M; p.N = 4 * d; p.K = d; p.split_k = 1; p.alpha = 1.f;
+  p.ff_stats = const_cast<float*>(stats); p.ff_ab = ab; p.ff_hidden = 4 * d;
+  p.ff_u = reinterpret_cast<const bf16*>(u); p.ff_ldu = ldu;
+  return launch_pair_ff<PEPI_FF_BWD, kMajorMN>(tmA, tmB, tmC, tmC, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -63,6 +63,9 @@ struct GemmParams {
   float* ff_stats;         // DOWN: [M,2] (mean, rstd) of the GEGLU output rows, written for the backward
   float ff_eps;            // LayerNorm epsilon
   int ff_hidden;           // 4*dim: LayerNorm width; column offset of the gate half inside u
+  const bf16* ff_u;        // BWD: saved [value | gate] activations [M, 8d]
+  long long ff_ldu;
+  const float* ff_ab;      // BWD: [M,2] per-row (mean_k(gdh), mean_k(gdh * hn)) from xclip_ff_bwd_prep
 };
 
 constexpr int EPI_STORE = 0;    // C = alpha*acc (+bias) (+residual)

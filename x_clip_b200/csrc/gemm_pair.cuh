@@ -23,6 +23,14 @@
 //                x2 = LN(hp) g W2^T + x1 = rstd_r (acc_rj - mean_r c_j) + x1_rj  with
 //                acc = hp (W2 . g)^T and c_j = sum_k (W2 . g)_jk; also writes bf16(acc) and
 //                (mean, rstd) for the backward.
+//   PEPI_FF_BWD  backward of LayerNorm(4d) + GEGLU fused into the down-projection's dgrad GEMM
+//                gdh = dx (W2 . g): per element
+//                  hn = (value*gelu(gate) - mean) rstd;  dhp = rstd (gdh - a_r - hn b_r)
+//                  d value = dhp gelu(gate);  d gate = dhp value gelu'(gate)
+//                with the two row means a_r = mean_k gdh, b_r = mean_k gdh*hn supplied by
+//                xclip_ff_bwd_prep (they only need the d-wide vectors dx, W2g row sums and the saved
+//                down-projection accumulator).  Reads u = [value | gate], writes du - the [M, 4d]
+//                gradient dh and the separate geglu_ln_bwd pass disappear.
 #pragma once
 
 #include "gemm.cuh"
@@ -32,18 +40,20 @@ namespace xclip {
 constexpr int PEPI_STORE = 0;
 constexpr int PEPI_FF_UP = 1;
 constexpr int PEPI_FF_DOWN = 2;
+constexpr int PEPI_FF_BWD = 3;
 
 template <int EPI>
 struct PairCfg {
-  static constexpr int kEpiWarps = EPI == PEPI_FF_UP ? 8 : 4;
+  static constexpr int kEpiWarps = (EPI == PEPI_FF_UP || EPI == PEPI_FF_BWD) ? 8 : 4;
   static constexpr int kThreads = (kEpiWarps + 2) * 32;
   static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB: this CTA's 128 rows of A
   static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBox = 128 * 128;                          // one [128 rows x 64 bf16] staging box
   // STORE: 2 boxes (double buffered); FF_UP: (value, gate, hp) x 2 column halves; FF_DOWN: (out, acc)
-  static constexpr int kStagingBytes = (EPI == PEPI_FF_UP ? 6 : 2) * kBox;
-  static constexpr int kStages = EPI == PEPI_FF_UP ? 4 : 6;
+  // FF_BWD: (d value, d gate) x 2 column halves
+  static constexpr int kStagingBytes = (EPI == PEPI_FF_UP ? 6 : (EPI == PEPI_FF_BWD ? 4 : 2)) * kBox;
+  static constexpr int kStages = EPI == PEPI_FF_UP ? 4 : (EPI == PEPI_FF_BWD ? 5 : 6);
   static constexpr int kBarrierBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
 };
@@ -112,7 +122,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != PEPI_STORE || p.use_tma_store) tma_prefetch_desc(&tmC);
-    if (EPI != PEPI_STORE) tma_prefetch_desc(&tmC2);
+    if (EPI == PEPI_FF_UP || EPI == PEPI_FF_DOWN) tma_prefetch_desc(&tmC2);
   }
   if (warp == kEpiWarps + 1) tmem_alloc_pair_512(tmem_slot);
   tcgen05_fence_before();
@@ -263,6 +273,60 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row), "f"(s1) : "memory");
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row + 1), "f"(s2) : "memory");
         }
+      } else if constexpr (EPI == PEPI_FF_BWD) {
+        // tile columns = hidden units [256 n_blk, +256); this warp's half: +[128 half, +128)
+        const uint32_t stg = smem_u32(smem_c) + half * 2 * S::kBox;   // d value | d gate boxes
+        const bool issuer = (threadIdx.x == half * 128);
+        float mean = 0.f, rstd = 0.f, am = 0.f, bm = 0.f;
+        if (row_ok) {
+          const float2 st = *reinterpret_cast<const float2*>(p.ff_stats + 2ll * row);
+          const float2 ab = *reinterpret_cast<const float2*>(p.ff_ab + 2ll * row);
+          mean = st.x; rstd = st.y; am = ab.x; bm = ab.y;
+        }
+        const bf16* urow = p.ff_u + (long long)(row_ok ? row : 0) * p.ff_ldu;
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          const int kq = n_blk * BLOCK_N + half * 128 + q * 64;
+#pragma unroll
+          for (int c32 = 0; c32 < 2; ++c32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + half * 128 + q * 64 + c32 * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const int k0 = kq + c32 * 32 + i;
+              const uint4 rv = *reinterpret_cast<const uint4*>(urow + k0);
+              const uint4 rg = *reinterpret_cast<const uint4*>(urow + p.ff_hidden + k0);
+              const uint32_t wv[4] = {rv.x, rv.y, rv.z, rv.w}, wg[4] = {rg.x, rg.y, rg.z, rg.w};
+              float dv[8], dg[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float2 pv = unpack_bf16x2(wv[e >> 1]), pg = unpack_bf16x2(wg[e >> 1]);
+                const float val = (e & 1) ? pv.y : pv.x, gate = (e & 1) ? pg.y : pg.x;
+                const GeluParts gp = gelu_parts(gate);
+                const float ge = gate * gp.cdf;                       // gelu(gate)
+                const float gd = fmaf(gate, gp.pdf, gp.cdf);          // gelu'(gate)
+                const float hn = (val * ge - mean) * rstd;
+                const float dhp = rstd * (__uint_as_float(v[i + e]) - am - hn * bm);
+                dv[e] = dhp * ge;
+                dg[e] = dhp * val * gd;
+              }
+              const int chunk = c32 * 4 + (i >> 3);
+              st_box_bf16x8(stg, row_in_tile, chunk, dv);
+              st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, dg);
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          if (issuer) {
+            const int r0 = m_blk * kGemmBlockM;
+            tma_store_2d(&tmC, stg, kq, r0);                        // du[:, k ..]        d value
+            tma_store_2d(&tmC, stg + S::kBox, p.ff_hidden + kq, r0);   // du[:, 4d + k ..]   d gate
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       } else {   // PEPI_FF_DOWN
         const uint32_t stg = smem_u32(smem_c);                  // out box | acc box
         const float invD = 1.f / (float)p.ff_hidden;
@@ -329,7 +393,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
     }
     // outstanding TMA stores must have READ their staging smem before the CTA exits
-    if (EPI == PEPI_FF_UP) {
+    if (EPI == PEPI_FF_UP || EPI == PEPI_FF_BWD) {
       if ((threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if ((EPI != PEPI_STORE || p.use_tma_store) && threadIdx.x == 0) {
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -455,6 +455,89 @@ l2norm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ z,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused feed-forward backward helpers (see csrc/ff.cu).  The LayerNorm(4d) output h is never
+// materialised; its backward only needs d-wide row quantities:
+//   dxs   = bf16(dx * rstd_r)                       operand of dW2g = dxs^T hp - vsum (x) 1
+//   vsum  = sum_r dxs_r * mean_r                     [d]
+//   ab[r] = (a/D, rstd (t - mean a)/D),  a = <dx_r, colvec>,  t = <dx_r, acc_r>     (D = 4 d)
+//           = the two row means mean_k(gdh) and mean_k(gdh * hn) of the LayerNorm backward, because
+//             gdh = dx W2g and sum_k hn_k W2g_jk = (x2 - x1)_j = rstd (acc_j - mean colvec_j).
+// ---------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+ff_bwd_prep_kernel(const bf16* __restrict__ dx, long long lddx, const float* __restrict__ stats,
+                   const bf16* __restrict__ acc, long long ldacc, const float* __restrict__ colvec,
+                   bf16* __restrict__ dxs, float* __restrict__ vsum, float* __restrict__ ab, int rows) {
+  __shared__ float red[NV * 256];
+  constexpr int D = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * kRowWarps;
+  float vacc[NV][8], cv[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { vacc[j][e] = 0.f; cv[j][e] = 0.f; }
+    if (colvec != nullptr) loadf8(colvec + (j * 32 + lane) * 8, cv[j]);
+  }
+  const float invD4 = 1.f / (4.f * D);
+  for (long long row = warp_global; row < rows; row += warp_stride) {
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float a = 0.f, t = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (j * 32 + lane) * 8;
+      float f[8];
+      load8(dx + row * lddx + col, f);
+      if (ab != nullptr) {
+        float ac[8];
+        load8(acc + row * ldacc + col, ac);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a = fmaf(f[e], cv[j][e], a); t = fmaf(f[e], ac[e], t); }
+      }
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o[e] = bf16_round(f[e] * rstd);
+        vacc[j][e] = fmaf(o[e], mean, vacc[j][e]);
+      }
+      store8(dxs + row * D + col, o);
+    }
+    if (ab != nullptr) {
+      a = warp_sum(a);
+      t = warp_sum(t);
+      if (lane == 0) {
+        ab[2 * row] = a * invD4;
+        ab[2 * row + 1] = rstd * (t - mean * a) * invD4;
+      }
+    }
+  }
+  flush_column_partials<NV>(vacc, vsum, red);
+}
+
+// raw = dxs^T hp (f32 [d, 4d]).  In place: dW2[j,k] = g[k] (raw[j,k] - vsum[j]);  optionally
+// dg[k] += sum_j (raw[j,k] - vsum[j]) * w2[j,k]   (gain gradient of the folded LayerNorm).
+// One thread per column k, blockIdx.y walks row chunks.
+__global__ void __launch_bounds__(256)
+ff_w2_grad_post_kernel(float* __restrict__ raw, const float* __restrict__ vsum,
+                       const float* __restrict__ g, const float* __restrict__ w2,
+                       float* __restrict__ dg, int d, int rows_per_block) {
+  const long long D4 = 4ll * d;
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= D4) return;
+  const int j0 = blockIdx.y * rows_per_block;
+  const int j1 = min(j0 + rows_per_block, d);
+  const float gk = g[k];
+  float acc = 0.f;
+  for (int j = j0; j < j1; ++j) {
+    const float t = raw[j * D4 + k] - vsum[j];
+    if (w2 != nullptr) acc = fmaf(t, w2[j * D4 + k], acc);
+    raw[j * D4 + k] = gk * t;
+  }
+  if (dg != nullptr) atomicAdd(dg + k, acc);
+}
+
 // flat fp32 -> bf16
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
@@ -695,5 +778,40 @@ extern "C" int xclip_adamw_step(float* p, const float* g, float* m, float* v, in
       p, g, m, v, n4, n, lr, beta1, beta2, eps, 1.f - lr * weight_decay, (float)(lr / bc1),
       (float)(1.0 / sqrt(bc2)), grad_scale);
   XCLIP_LAUNCH_CHECK("adamw_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_ff_bwd_prep(const void* dx, int64_t lddx, const float* stats, const void* acc,
+                                 int64_t ldacc, const float* colvec, void* dxs, float* vsum, float* ab,
+                                 int rows, int d, xclip_stream_t stream) {
+  using namespace xclip;
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(dx && stats && dxs && vsum && rows > 0, "ff_bwd_prep: bad arguments");
+  XCLIP_REQUIRE(d % 256 == 0, "ff_bwd_prep: d=%d must be a multiple of 256", d);
+  XCLIP_REQUIRE(ab == nullptr || (acc && colvec), "ff_bwd_prep: ab needs acc and colvec");
+  XCLIP_REQUIRE(lddx % 8 == 0 && lddx >= d && ALIGNED16(dx) && ALIGNED16(dxs) &&
+                    (!acc || (ALIGNED16(acc) && ldacc % 8 == 0 && ldacc >= d)) && (!colvec || ALIGNED16(colvec)),
+                "ff_bwd_prep: misaligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = row_grid(rows) < num_sms() * 4 ? row_grid(rows) : num_sms() * 4;
+  DISPATCH_NARROW(ff_bwd_prep_kernel, d, grid, s, (const bf16*)dx, lddx, stats, (const bf16*)acc, ldacc,
+                  colvec, (bf16*)dxs, vsum, ab, rows)
+  XCLIP_LAUNCH_CHECK("ff_bwd_prep_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float* g, const float* w2,
+                                     float* dg, int d, xclip_stream_t stream) {
+  using namespace xclip;
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(raw && vsum && g && d > 0 && d % 256 == 0, "ff_w2_grad_post: bad arguments");
+  XCLIP_REQUIRE((dg == nullptr) == (w2 == nullptr), "ff_w2_grad_post: dg and w2 go together");
+  const int rows_per_block = 64;
+  dim3 grid((4 * d + 255) / 256, (d + rows_per_block - 1) / rows_per_block);
+  ff_w2_grad_post_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(raw, vsum, g, w2, dg, d,
+                                                                                 rows_per_block);
+  XCLIP_LAUNCH_CHECK("ff_w2_grad_post_kernel");
   return XCLIP_OK;
 }

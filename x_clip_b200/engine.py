@@ -145,7 +145,7 @@ class TransformerFn(torch.autograd.Function):
         x_in = x_in.contiguous()
         mask_c = None if mask is None else mask.contiguous()
 
-        saved = []
+        saved, ff_saved = [], []
         # bf16 MMA operands of this call's weights; backward reuses exactly these (ctx.wb)
         wb = [tuple(weight_bf16(w) for w in (l[1], l[2], l[5], l[7])) for l in layers]
         # norm_in fused with the first pre-norm
@@ -164,7 +164,8 @@ class TransformerFn(torch.autograd.Function):
                 # the down-projection); the backward knows from ctx.fused_ff
                 w1p, w2g, colvec = ff_weights(w1, w2, g4)
                 u, h, rowsum = K.ff_up(xn2, w1p)
-                x2, _acc, st_v = K.ff_down(h, w2g, colvec, rowsum, x1, LN_EPS)
+                x2, acc, st_v = K.ff_down(h, w2g, colvec, rowsum, x1, LN_EPS)
+                ff_saved.append((w2g, colvec, acc))
             else:
                 u = K.gemm(xn2, b1)
                 h, st_v = K.geglu_ln_fwd(u, g4, eps=LN_EPS)
@@ -181,6 +182,7 @@ class TransformerFn(torch.autograd.Function):
         ctx.dims = (B, n, d, heads, depth, scale, causal)
         ctx.rot = (rot_cos, rot_sin)
         ctx.fused_ff = FUSED_FF
+        ctx.ff_saved = ff_saved
         ctx.weights = weights
         ctx.wb = wb
         return out.view(B, n, d)
@@ -212,15 +214,20 @@ class TransformerFn(torch.autograd.Function):
             bqkv, bo, b1, b2 = ctx.wb[L]
             base = 2 + 8 * L
             # feed-forward: x2 = h @ w2^T + x1
-            dh = K.gemm(dx, b2, b_major=1)
-            if ctx.fused_ff:
-                # h is the pre-norm hp: dW2 = g4 * (dxs^T hp - vsum (x) 1), dxs = dx * rstd
-                dxs, vsum = K.ff_bwd_prep(dx, st_v)
-                grads[base + 7] = K.ff_w2_grad_post_(wg.wgrad(dxs, h), vsum, g4.detach())
-            else:
-                grads[base + 7] = wg.wgrad(dx, h)
             dg4 = torch.zeros(g4.shape[0], device=dev, dtype=F32)
-            du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
+            if ctx.fused_ff:
+                # h is the pre-norm hp.  Row means of the LayerNorm backward from d-wide data, the
+                # LN + GEGLU backward inside the dgrad GEMM, dW2 / dg4 from dW2g = dxs^T hp - vsum
+                w2g, colvec, acc = ctx.ff_saved[L]
+                ctx.ff_saved[L] = None
+                dxs, vsum, ab = K.ff_bwd_prep(dx, st_v, acc, colvec)
+                du = K.ff_bwd(dx, w2g, u, st_v, ab)
+                grads[base + 7] = K.ff_w2_grad_post_(wg.wgrad(dxs, h), vsum, g4.detach(), w2.detach(), dg4)
+                dh = None
+            else:
+                dh = K.gemm(dx, b2, b_major=1)
+                grads[base + 7] = wg.wgrad(dx, h)
+                du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
             grads[base + 6] = dg4
             del dh
             dxn2 = K.gemm(du, b1, b_major=1)

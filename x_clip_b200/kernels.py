@@ -291,22 +291,44 @@ def ff_down(hp, w2g, colvec, rowsum, res, eps):
     return out, acc, stats
 
 
-def ff_bwd_prep(dx, stats):
-    """-> (dxs bf16 [M,d] = dx * rstd, vsum f32 [d] = sum_r dxs[r] * mean_r)."""
+def ff_bwd_prep(dx, stats, acc=None, colvec=None):
+    """-> (dxs bf16 [M,d] = dx * rstd, vsum f32 [d] = sum_r dxs[r] * mean_r, ab f32 [M,2] or None:
+    the two row means of the LayerNorm backward, computed when acc and colvec are given)."""
     _need(dx, BF16, "dx"); _rows2d(dx, "dx"); _need(stats, F32, "stats")
     M, d = dx.shape
     dxs = torch.empty((M, d), device=dx.device, dtype=BF16)
     vsum = torch.zeros((d,), device=dx.device, dtype=F32)
-    _call(dx, "ff_small", 0.0, 4.0 * M * d, "xclip_ff_bwd_prep", dx.data_ptr(), dx.stride(0),
-          stats.data_ptr(), dxs.data_ptr(), vsum.data_ptr(), M, d)
-    return dxs, vsum
+    ab = None
+    if acc is not None:
+        _need(acc, BF16, "acc"); _rows2d(acc, "acc"); _need(colvec, F32, "colvec")
+        ab = torch.empty((M, 2), device=dx.device, dtype=F32)
+    _call(dx, "ff_small", 0.0, (4.0 + (2.0 if acc is not None else 0.0)) * M * d, "xclip_ff_bwd_prep",
+          dx.data_ptr(), dx.stride(0), stats.data_ptr(), _ptr(acc), acc.stride(0) if acc is not None else 0,
+          _ptr(colvec), dxs.data_ptr(), vsum.data_ptr(), _ptr(ab), M, d)
+    return dxs, vsum, ab
 
 
-def ff_w2_grad_post_(raw, vsum, g4):
+def ff_bwd(dx, w2g, u, stats, ab):
+    """du bf16 [M,8d]: LayerNorm(4d) + GEGLU backward fused into the dgrad GEMM dx @ w2g."""
+    _need(dx, BF16, "dx"); _rows2d(dx, "dx"); _need(w2g, BF16, "w2g"); _need(u, BF16, "u"); _rows2d(u, "u")
+    _need(stats, F32, "stats"); _need(ab, F32, "ab")
+    M, d = dx.shape
+    du = torch.empty((M, 8 * d), device=dx.device, dtype=BF16)
+    _call(dx, "gemm_dgrad", 2.0 * M * 4 * d * d, 2.0 * (M * d + 4 * d * d + 16 * M * d), "xclip_ff_bwd",
+          dx.data_ptr(), dx.stride(0), w2g.data_ptr(), u.data_ptr(), u.stride(0), stats.data_ptr(),
+          ab.data_ptr(), du.data_ptr(), du.stride(0), M, d)
+    return du
+
+
+def ff_w2_grad_post_(raw, vsum, g4, w2=None, dg=None):
+    """In place dW2 = g4 * (raw - vsum (x) 1); with w2/dg also accumulates the gain gradient."""
     _need(raw, F32, "raw"); _need(vsum, F32, "vsum"); _need(g4, F32, "g4")
     d = raw.shape[0]
-    _call(raw, "ff_small", 0.0, 8.0 * raw.numel(), "xclip_ff_w2_grad_post", raw.data_ptr(), vsum.data_ptr(),
-          g4.data_ptr(), d)
+    if w2 is not None:
+        _need(w2, F32, "w2"); _need(dg, F32, "dg")
+        w2 = w2.contiguous()
+    _call(raw, "ff_small", 0.0, (8.0 + (4.0 if w2 is not None else 0.0)) * raw.numel(), "xclip_ff_w2_grad_post",
+          raw.data_ptr(), vsum.data_ptr(), g4.data_ptr(), _ptr(w2), _ptr(dg), d)
     return raw
 
 
