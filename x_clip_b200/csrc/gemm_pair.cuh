@@ -274,8 +274,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row + 1), "f"(s2) : "memory");
         }
       } else if constexpr (EPI == PEPI_FF_BWD) {
-        // tile columns = hidden units [256 n_blk, +256); this warp's half: +[128 half, +128)
-        const uint32_t stg = smem_u32(smem_c) + half * 2 * S::kBox;   // d value | d gate boxes
+        // tile columns = hidden units [256 n_blk, +256); this warp's half: +[128 half, +128).
+        // u = [value | gate] is read COALESCED (a warp reads its 32 rows x 128 B per box) into the
+        // warp's own 32-row slab of the staging boxes, which have exactly the layout the TMA store
+        // wants; each lane then picks up its row, and the gradients overwrite the slab in place.
+        // (A lane reading its own row straight from global memory costs 32 L1 wavefronts per
+        // request - 8 k cycles per tile, more than the tile's MMAs.)
+        const uint32_t stg = smem_u32(smem_c) + half * 2 * S::kBox;   // value -> d value | gate -> d gate
         const bool issuer = (threadIdx.x == half * 128);
         float mean = 0.f, rstd = 0.f, am = 0.f, bm = 0.f;
         if (row_ok) {
@@ -283,12 +288,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float2 ab = *reinterpret_cast<const float2*>(p.ff_ab + 2ll * row);
           mean = st.x; rstd = st.y; am = ab.x; bm = ab.y;
         }
-        const bf16* urow = p.ff_u + (long long)(row_ok ? row : 0) * p.ff_ldu;
+        const int slab_row0 = m_blk * kGemmBlockM + quarter * 32;      // first global row of the slab
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
           const int kq = n_blk * BLOCK_N + half * 128 + q * 64;
+          // coalesced fetch: iteration t covers slab rows 4t..4t+3, lane = (row%4)*8 + chunk
+          uint4 rawv[8], rawg[8];
+#pragma unroll
+          for (int t8 = 0; t8 < 8; ++t8) {
+            const int rr = slab_row0 + t8 * 4 + (lane >> 3);
+            const bf16* src = p.ff_u + (long long)(rr < p.M ? rr : 0) * p.ff_ldu + kq + (lane & 7) * 8;
+            rawv[t8] = *reinterpret_cast<const uint4*>(src);
+            rawg[t8] = *reinterpret_cast<const uint4*>(src + p.ff_hidden);
+          }
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // previous stores have read the boxes
+#pragma unroll
+          for (int t8 = 0; t8 < 8; ++t8) {
+            const int r = quarter * 32 + t8 * 4 + (lane >> 3);
+            const uint32_t off = swz128(r, lane & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(rawv[t8].x),
+                         "r"(rawv[t8].y), "r"(rawv[t8].z), "r"(rawv[t8].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(rawg[t8].x),
+                         "r"(rawg[t8].y), "r"(rawg[t8].z), "r"(rawg[t8].w) : "memory");
+          }
+          __syncwarp();
 #pragma unroll
           for (int c32 = 0; c32 < 2; ++c32) {
             uint32_t v[32];
@@ -296,10 +320,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-              const int k0 = kq + c32 * 32 + i;
-              const uint4 rv = *reinterpret_cast<const uint4*>(urow + k0);
-              const uint4 rg = *reinterpret_cast<const uint4*>(urow + p.ff_hidden + k0);
-              const uint32_t wv[4] = {rv.x, rv.y, rv.z, rv.w}, wg[4] = {rg.x, rg.y, rg.z, rg.w};
+              const int chunk = c32 * 4 + (i >> 3);
+              const uint32_t off = swz128(row_in_tile, chunk);
+              uint32_t wv[4], wg[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(stg + off));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(wg[0]), "=r"(wg[1]), "=r"(wg[2]), "=r"(wg[3]) : "r"(stg + S::kBox + off));
               float dv[8], dg[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -313,7 +340,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 dv[e] = dhp * ge;
                 dg[e] = dhp * val * gd;
               }
-              const int chunk = c32 * 4 + (i >> 3);
               st_box_bf16x8(stg, row_in_tile, chunk, dv);
               st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, dg);
             }
