@@ -47,7 +47,7 @@ long long xclip_launch_count(void);
 void xclip_launch_count_reset(void);
 
 /* ---- dense contraction (tcgen05) --------------------------------------
- * C[M,N] (+)= alpha * A * B^T (+ bias[N]) (+ residual[row % res_row_mod or row, N])
+ * C[M,N] (+)= alpha * A * B^T (+ bias[N]) (+ residual[res_row_idx[row] | row % res_row_mod | row, N])
  * Replaces nn.Linear fwd + its autograd dgrad/wgrad:
  *   x_clip/x_clip.py:191,195 (FeedForward), :209,:210 (Attention to_qkv/to_out),
  *   :358 (patch embedding, with bias), :368 (to_cls_tokens), :556,:570 (latent proj).
@@ -66,7 +66,8 @@ int xclip_gemm_set_pair_mode(int enabled);
 int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb,
                     int b_major, void* c, int64_t ldc, int c_dtype, int M, int N, int K,
                     float alpha, const float* bias, const void* residual, int64_t ldr,
-                    int res_row_mod, int accumulate, xclip_stream_t stream);
+                    int res_row_mod, const int32_t* res_row_idx, int accumulate,
+                    xclip_stream_t stream);
 
 /* ---- row-wise kernels ---------------------------------------------------
  * Gain-only LayerNorm, biased variance (x_clip/x_clip.py:112-121).  One call can also apply
@@ -228,6 +229,19 @@ int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float* g, const f
 int xclip_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale,
                      xclip_stream_t stream);
+
+/* ---- patch-embedding front end (x_clip/x_clip.py:356-359 patchify, :134-151 PatchDropout) -------
+ * patchify_gather : img f32 [B,C,H,W] -> bf16 [B*k, patch*patch*C] rows in the reference's
+ *                   (p1 p2 c) order for the patches keep[b, j] (int64 [B,k]; NULL = all k = n patches,
+ *                   in order): only kept patches are read and embedded.
+ * scatter_add_rows: dst f32 [V,d] rows idx[r] (or r %% period) += src bf16 [rows,d]  (gradient of the
+ *                   gathered position table);  colsum_rows: dst[d] += column sums (bias gradient). */
+int xclip_patchify_gather(const float* img, int B, int C, int H, int W, int patch, const int64_t* keep,
+                          int k, void* out, xclip_stream_t stream);
+int xclip_scatter_add_rows(const int32_t* idx, int period, const void* src, int64_t lds, float* dst,
+                           int64_t rows, int d, int V, xclip_stream_t stream);
+int xclip_colsum_rows(const void* src, int64_t lds, float* dst, int64_t rows, int d,
+                      xclip_stream_t stream);
 
 /* ---- rotary position embedding (x_clip/x_clip.py:155-176, applied to q, k and v at :221-223) ----
  * In place on the bf16 qkv buffer [rows, ld] (rows = B*n tokens, position = row %% n): in each of

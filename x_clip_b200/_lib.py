@@ -31,7 +31,12 @@ SIGNATURES = {
     "xclip_gemm_set_pair_mode": (c_int, [c_int]),
     "xclip_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
                                 c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
-                                c_int64, c_int, c_int, c_void_p]),
+                                c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "xclip_patchify_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                      c_void_p]),
+    "xclip_scatter_add_rows": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
+                                       c_void_p]),
+    "xclip_colsum_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "xclip_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                     c_int, c_int, c_float, c_void_p]),

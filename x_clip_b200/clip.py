@@ -142,15 +142,21 @@ class PatchDropout(nn.Module):
         self.prob = prob
         self.forced_keep: Optional[torch.Tensor] = None
 
-    def forward(self, x, force_keep_all: bool = False):
+    def indices(self, b: int, n: int, device, force_keep_all: bool = False) -> Optional[torch.Tensor]:
+        """Kept patch indices int64 [b, keep] drawn exactly like the reference (:146-149), or None
+        when every patch is kept (eval mode, prob 0, keep_all_patches)."""
         if not self.training or self.prob == 0. or force_keep_all:
-            return x
-        b, n, d = x.shape
+            return None
         keep = max(1, int(n * (1 - self.prob)))
         if self.forced_keep is not None:
-            idx = self.forced_keep.to(x.device)
-        else:
-            idx = torch.randn(b, n, device=x.device).topk(keep, dim=-1).indices
+            return self.forced_keep.to(device)
+        return torch.randn(b, n, device=device).topk(keep, dim=-1).indices
+
+    def forward(self, x, force_keep_all: bool = False):
+        b, n, d = x.shape
+        idx = self.indices(b, n, x.device, force_keep_all)
+        if idx is None:
+            return x
         return torch.gather(x, 1, idx[:, :, None].expand(-1, -1, d))
 
 
@@ -223,23 +229,27 @@ class VisionTransformer(nn.Module):
         self.transformer = Transformer(dim, **kwargs)
         self.to_cls_tokens = nn.Sequential(_Slot(), nn.Linear(dim, dim, bias=False), _Slot())
 
-    def patchify(self, img: torch.Tensor) -> torch.Tensor:
-        """[b, c, H, W] -> bf16 [b * (H/p)*(W/p), p*p*c] with the reference's (p1 p2 c) order."""
-        b, c, H, W = img.shape
-        p = self.patch_size
-        x = img.to(BF16).view(b, c, H // p, p, W // p, p).permute(0, 2, 4, 3, 5, 1)
-        return x.reshape(b * (H // p) * (W // p), p * p * c)
-
     def forward(self, x, keep_all_patches: bool = False):
+        """image f32 [b, c, H, W] -> [b, 1 + n_kept, dim] (CLS first).  Patchify, PatchDropout and the
+        bf16 cast are ONE pass that reads only the kept patches (xclip_patchify_gather); the
+        patch-embedding GEMM adds bias and the gathered position rows in its epilogue."""
         b = x.shape[0]
-        lin = self.to_tokens[1]
-        patches = self.patchify(x)
-        n = patches.shape[0] // b
+        _require(x.is_cuda, "inputs must live on a CUDA (sm_100) device")
+        p = self.patch_size
+        _require(x.shape[2] % p == 0 and x.shape[3] % p == 0, "image size must be a multiple of the patch size")
+        n = (x.shape[2] // p) * (x.shape[3] // p)
         _require(n == self.pos_emb.num_embeddings, "image size does not match the position table")
-        tok = E.LinearFn.apply(patches, lin.weight, lin.bias, self.pos_emb.weight)
-        tok = tok.view(b, n, -1)
-        tok = self.patch_dropout(tok, force_keep_all=keep_all_patches)
-        out = self.transformer(tok)
+        lin = self.to_tokens[1]
+        keep = self.patch_dropout.indices(b, n, x.device, keep_all_patches)
+        if keep is None:
+            index = torch.arange(n, device=x.device, dtype=torch.int32).repeat(b)
+            k = n
+        else:
+            index = keep.reshape(-1).to(torch.int32)
+            k = keep.shape[1]
+        patches = E.K.patchify_gather(x.float(), p, keep)
+        tok = E.PatchEmbedFn.apply(patches, index, lin.weight, lin.bias, self.pos_emb.weight)
+        out = self.transformer(tok.view(b, k, -1))
         pooled = out.float().mean(dim=1).to(BF16)
         cls = E.LinearFn.apply(pooled, self.to_cls_tokens[1].weight, None, None)
         return torch.cat((cls[:, None], out), dim=1)

@@ -216,3 +216,136 @@ extern "C" int xclip_rotary_inplace(void* qkv, int64_t ld, int64_t rows, int n, 
   XCLIP_LAUNCH_CHECK("rotary_inplace_kernel");
   return XCLIP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Patch embedding front end (x_clip/x_clip.py:356-359 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' and
+// PatchDropout :134-151): one pass from the fp32 image to the bf16 A operand of the patch-embedding
+// GEMM, reading ONLY the kept patches (keep[b, j] = patch index, or all patches in order when NULL).
+// Mathematically the reference embeds every patch and drops half afterwards; embedding only the
+// kept ones gives the same tokens (the position-table row is selected by the same index).
+// ---------------------------------------------------------------------------------------------
+namespace xclip {
+__global__ void __launch_bounds__(256)
+patchify_gather_kernel(const float* __restrict__ img, int B, int C, int H, int W, int P,
+                       const long long* __restrict__ keep, int k, int n_patches,
+                       bf16* __restrict__ out) {
+  const int gw_n = W / P;
+  const int patch_dim = P * P * C;
+  const int vec_per_row = patch_dim / 8;
+  const long long total = (long long)B * k * vec_per_row;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / vec_per_row;
+    const int e0 = (int)(idx - row * vec_per_row) * 8;
+    const long long b = row / k;
+    long long pidx = keep ? keep[row] : (row - b * k);
+    if (pidx < 0 || pidx >= n_patches) __trap();
+    const int gh = (int)(pidx / gw_n), gw = (int)(pidx - (long long)gh * gw_n);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int el = e0 + e;
+      const int q = el / C, c = el - q * C;
+      const int p1 = q / P, p2 = q - p1 * P;
+      f[e] = __ldg(img + ((b * C + c) * H + gh * P + p1) * (long long)W + gw * P + p2);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + row * patch_dim + e0) = o;
+  }
+}
+
+// dst[idx[r] or r %% period, :] += src[r, :]  (f32 += bf16): gradient of a gathered / periodic table
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const int* __restrict__ idx, int period, const bf16* __restrict__ src,
+                        long long lds, float* __restrict__ dst, long long rows, int d, int V) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const long long t = idx ? idx[r] : (r % period);
+    if (t < 0 || t >= V) __trap();
+    const bf16* s = src + r * lds;
+    float* o = dst + t * d;
+    for (int c = lane * 8; c < d; c += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(s + c);
+      const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z),
+                   dd = unpack_bf16x2(u.w);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c), "f"(a.x), "f"(a.y),
+                   "f"(bb.x), "f"(bb.y) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c + 4), "f"(cc.x), "f"(cc.y),
+                   "f"(dd.x), "f"(dd.y) : "memory");
+    }
+  }
+}
+
+// dst[c] += sum_r src[r, c]   (bias gradient): block (column chunk, row slice)
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const bf16* __restrict__ src, long long lds, float* __restrict__ dst, long long rows,
+                   int d, int slices) {
+  const int c = blockIdx.x * 512 + threadIdx.x * 2;
+  if (c >= d) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (long long r = blockIdx.y; r < rows; r += slices) {
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + r * lds + c));
+    s0 += v.x;
+    s1 += v.y;
+  }
+  atomicAdd(dst + c, s0);
+  atomicAdd(dst + c + 1, s1);
+}
+}  // namespace xclip
+
+extern "C" int xclip_patchify_gather(const float* img, int B, int C, int H, int W, int patch,
+                                     const int64_t* keep, int k, void* out, xclip_stream_t stream) {
+  using namespace xclip;
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(img && out && B > 0 && C > 0 && patch > 0 && H % patch == 0 && W % patch == 0,
+                "patchify: bad arguments");
+  const int n_patches = (H / patch) * (W / patch);
+  XCLIP_REQUIRE((patch * patch * C) % 8 == 0, "patchify: channels*patch^2 must be a multiple of 8");
+  XCLIP_REQUIRE(k > 0 && (keep != nullptr || k == n_patches), "patchify: k=%d", k);
+  XCLIP_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "patchify: misaligned output");
+  const long long total = (long long)B * k * (patch * patch * C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  patchify_gather_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, B, C, H, W, patch, reinterpret_cast<const long long*>(keep), k, n_patches,
+      reinterpret_cast<bf16*>(out));
+  XCLIP_LAUNCH_CHECK("patchify_gather_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_scatter_add_rows(const int32_t* idx, int period, const void* src, int64_t lds,
+                                      float* dst, int64_t rows, int d, int V, xclip_stream_t stream) {
+  using namespace xclip;
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(src && dst && rows > 0 && d % 8 == 0 && V > 0 && (idx != nullptr || period > 0),
+                "scatter_add_rows: bad arguments");
+  XCLIP_REQUIRE(lds % 8 == 0 && lds >= d && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                "scatter_add_rows: misaligned");
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  scatter_add_rows_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      idx, period, reinterpret_cast<const bf16*>(src), lds, dst, rows, d, V);
+  XCLIP_LAUNCH_CHECK("scatter_add_rows_kernel");
+  return XCLIP_OK;
+}
+
+extern "C" int xclip_colsum_rows(const void* src, int64_t lds, float* dst, int64_t rows, int d,
+                                 xclip_stream_t stream) {
+  using namespace xclip;
+  int rc = xclip_init();
+  if (rc) return rc;
+  XCLIP_REQUIRE(src && dst && rows > 0 && d % 2 == 0, "colsum_rows: bad arguments");
+  int slices = (int)(rows < 256 ? rows : 256);
+  dim3 grid((d + 511) / 512, slices);
+  colsum_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src), lds, dst, rows, d, slices);
+  XCLIP_LAUNCH_CHECK("colsum_rows_kernel");
+  return XCLIP_OK;
+}

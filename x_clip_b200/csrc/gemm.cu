@@ -67,7 +67,8 @@ extern "C" int xclip_gemm_set_pair_mode(int enabled) {
 extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb,
                                int b_major, void* c, int64_t ldc, int c_dtype, int M, int N, int K,
                                float alpha, const float* bias, const void* residual, int64_t ldr,
-                               int res_row_mod, int accumulate, xclip_stream_t stream) {
+                               int res_row_mod, const int32_t* res_row_idx, int accumulate,
+                               xclip_stream_t stream) {
   using namespace xclip;
   int rc = xclip_init();
   if (rc) return rc;
@@ -151,6 +152,7 @@ extern "C" int xclip_gemm_bf16(const void* a, int64_t lda, int a_major, const vo
   p.c = c; p.ldc = ldc; p.c_is_f32 = c_dtype; p.atomic_add = accumulate ? 1 : 0;
   p.split_k = splits; p.alpha = alpha; p.bias = bias;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.res_row_mod = res_row_mod;
+  p.res_row_idx = res_row_idx;
 
   CUtensorMap tmC = tmA;   // placeholder unless the TMA-store epilogue is used
   if (c_dtype == 0) {

@@ -35,6 +35,7 @@ struct GemmParams {
   const bf16* residual;  // bf16 [*, N] or null
   long long ldr;
   int res_row_mod;     // residual row = row % res_row_mod when > 0 (positional tables)
+  const int* res_row_idx;  // or residual row = res_row_idx[row] (gathered positional rows), else row
   int use_tma_store;   // bf16 C written through swizzled smem staging + cp.async.bulk.tensor stores
   int raster_m_fast;   // tile order: 0 = N fastest (big A streamed once, B tile L2 resident),
                        //             1 = M fastest (small A resident, big B streamed once)
@@ -101,7 +102,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, const C
   const bool row_ok = row < p.M;
   const bf16* res_row = nullptr;
   if (p.residual != nullptr && row_ok) {
-    const long long rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    const long long rr = p.res_row_idx ? p.res_row_idx[row] : (p.res_row_mod > 0 ? (row % p.res_row_mod) : row);
     res_row = p.residual + rr * p.ldr;
   }
         if (p.use_tma_store) {

@@ -44,7 +44,10 @@ constexpr int PEPI_FF_BWD = 3;
 
 template <int EPI>
 struct PairCfg {
-  static constexpr int kEpiWarps = (EPI == PEPI_FF_UP || EPI == PEPI_FF_BWD) ? 8 : 4;
+  // the GELU epilogues are latency-bound (two MUFU + a dependent polynomial per element): with two
+  // warps per scheduler ncu showed 36 % issue-slot and 33 % XU utilisation while the tensor pipe idled
+  // a third of the time, so they get four warps per scheduler
+  static constexpr int kEpiWarps = (EPI == PEPI_FF_UP || EPI == PEPI_FF_BWD) ? 16 : 4;
   static constexpr int kThreads = (kEpiWarps + 2) * 32;
   static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KiB: this CTA's 128 rows of A
   static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
@@ -55,7 +58,8 @@ struct PairCfg {
   static constexpr int kStagingBytes = (EPI == PEPI_FF_UP ? 6 : (EPI == PEPI_FF_BWD ? 4 : 2)) * kBox;
   static constexpr int kStages = EPI == PEPI_FF_UP ? 4 : (EPI == PEPI_FF_BWD ? 5 : 6);
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
+  static constexpr int kScratchBytes = EPI == PEPI_FF_UP ? 2 * 128 * 8 : 0;   // row-sum exchange
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + kScratchBytes;
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -212,7 +216,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int it = 0;
     uint32_t store_count = 0;
     const int quarter = warp & 3;                 // TMEM lane quarter
-    const int half = warp >> 2;                   // FF_UP: which 64 hidden columns of the tile
     const int row_in_tile = quarter * 32 + lane;
     for (int t = pair; t < num_tiles; t += npairs, ++it) {
       const int tmn = t % (num_n * num_m2);
@@ -229,20 +232,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (EPI == PEPI_STORE) {
         gemm_epilogue_store<BLOCK_N>(p, tmC, smem_c, taddr, warp, lane, m_blk, n_blk, split, store_count);
       } else if constexpr (EPI == PEPI_FF_UP) {
-        // accumulator columns [0,128) = value, [128,256) = gate of hidden units [128 n_blk, +128)
-        const uint32_t stg = smem_u32(smem_c) + half * 3 * S::kBox;   // value | gate | hp boxes
-        const bool issuer = (threadIdx.x == half * 128);
+        // accumulator columns [0,128) = value, [128,256) = gate of hidden units [128 n_blk, +128).
+        // 16 warps: sub = warp>>2 owns hidden columns [32 sub, +32); subs {0,1} / {2,3} share one set
+        // of (value, gate, hp) boxes [128 rows x 64 columns].
+        const int sub = warp >> 2;
+        const int bs = sub >> 1;                                      // box set
+        const uint32_t stg = smem_u32(smem_c) + bs * 3 * S::kBox;     // value | gate | hp boxes
+        const bool issuer = (threadIdx.x == bs * 256);
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-          uint32_t vv[32], gg[32];
-          tmem_ld_32x32(taddr + half * 64 + c32 * 32, vv);
-          tmem_ld_32x32(taddr + 128 + half * 64 + c32 * 32, gg);
+        for (int c16 = 0; c16 < 2; ++c16) {
+          uint32_t vv[16], gg[16];
+          tmem_ld_32x16(taddr + sub * 32 + c16 * 16, vv);
+          tmem_ld_32x16(taddr + 128 + sub * 32 + c16 * 16, gg);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
+          for (int i = 0; i < 16; i += 8) {
             float va[8], ga[8], hp[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -252,36 +259,49 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               s1 += hp[e];
               s2 = fmaf(hp[e], hp[e], s2);
             }
-            const int chunk = c32 * 4 + (i >> 3);
+            const int chunk = (sub & 1) * 4 + c16 * 2 + (i >> 3);
             st_box_bf16x8(stg, row_in_tile, chunk, va);
             st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, ga);
             st_box_bf16x8(stg + 2 * S::kBox, row_in_tile, chunk, hp);
           }
         }
+        // the two warps sharing a row of this box set combine their partial sums (one red pair per
+        // row, box set and tile instead of two)
+        float2* xch = reinterpret_cast<float2*>(smem_c + S::kStagingBytes + S::kBarrierBytes) + bs * 128;
+        if (sub & 1) xch[row_in_tile] = make_float2(s1, s2);
         tcgen05_fence_before();
         fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
+        if (!(sub & 1)) {
+          const float2 o = xch[row_in_tile];
+          s1 += o.x;
+          s2 += o.y;
+        }
         if (issuer) {
-          const int hcol = n_blk * 128 + half * 64;            // hidden-unit column of this box
+          const int hcol = n_blk * 128 + bs * 64;               // hidden-unit column of this box
           const int r0 = m_blk * kGemmBlockM;
           tma_store_2d(&tmC, stg, hcol, r0);                    // u[:, hcol ..]            value
           tma_store_2d(&tmC, stg + S::kBox, p.ff_hidden + hcol, r0);   // u[:, 4d + hcol ..]  gate
           tma_store_2d(&tmC2, stg + 2 * S::kBox, hcol, r0);     // hp[:, hcol ..]
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (row_ok) {
+        if (row_ok && !(sub & 1)) {
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row), "f"(s1) : "memory");
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row + 1), "f"(s2) : "memory");
         }
       } else if constexpr (EPI == PEPI_FF_BWD) {
-        // tile columns = hidden units [256 n_blk, +256); this warp's half: +[128 half, +128).
-        // u = [value | gate] is read COALESCED (a warp reads its 32 rows x 128 B per box) into the
-        // warp's own 32-row slab of the staging boxes, which have exactly the layout the TMA store
-        // wants; each lane then picks up its row, and the gradients overwrite the slab in place.
-        // (A lane reading its own row straight from global memory costs 32 L1 wavefronts per
-        // request - 8 k cycles per tile, more than the tile's MMAs.)
-        const uint32_t stg = smem_u32(smem_c) + half * 2 * S::kBox;   // value -> d value | gate -> d gate
-        const bool issuer = (threadIdx.x == half * 128);
+        // tile columns = hidden units [256 n_blk, +256).  16 warps: sub = warp>>2; half = sub>>1 owns
+        // columns [128 half, +128) in two 64-column groups; the two subs of a half split each group
+        // (32 columns each).  u = [value | gate] is read COALESCED into the staging boxes, which have
+        // exactly the layout the TMA store wants (rows of a lane quarter are private to the two warps
+        // that share it); each lane then picks up its row and the gradients overwrite it in place.
+        // (A lane reading its own row straight from global memory costs 32 L1 wavefronts per request -
+        // 8 k cycles per tile, more than the tile's MMAs.)
+        const int sub = warp >> 2;
+        const int bhalf = sub >> 1;
+        const int part = sub & 1;                                      // which 32 columns of a group
+        const uint32_t stg = smem_u32(smem_c) + bhalf * 2 * S::kBox;   // value -> d value | gate -> d gate
+        const bool issuer = (threadIdx.x == bhalf * 256);
         float mean = 0.f, rstd = 0.f, am = 0.f, bm = 0.f;
         if (row_ok) {
           const float2 st = *reinterpret_cast<const float2*>(p.ff_stats + 2ll * row);
@@ -291,36 +311,37 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int slab_row0 = m_blk * kGemmBlockM + quarter * 32;      // first global row of the slab
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
-          const int kq = n_blk * BLOCK_N + half * 128 + q * 64;
-          // coalesced fetch: iteration t covers slab rows 4t..4t+3, lane = (row%4)*8 + chunk
-          uint4 rawv[8], rawg[8];
+          const int kq = n_blk * BLOCK_N + bhalf * 128 + q * 64;
+          // coalesced fetch: iteration t covers slab rows 4t..4t+3 (this warp: t = 4 part .. 4 part + 3),
+          // lane = (row%4)*8 + 16-byte chunk
+          uint4 rawv[4], rawg[4];
 #pragma unroll
-          for (int t8 = 0; t8 < 8; ++t8) {
-            const int rr = slab_row0 + t8 * 4 + (lane >> 3);
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int rr = slab_row0 + (part * 4 + t4) * 4 + (lane >> 3);
             const bf16* src = p.ff_u + (long long)(rr < p.M ? rr : 0) * p.ff_ldu + kq + (lane & 7) * 8;
-            rawv[t8] = *reinterpret_cast<const uint4*>(src);
-            rawg[t8] = *reinterpret_cast<const uint4*>(src + p.ff_hidden);
+            rawv[t4] = *reinterpret_cast<const uint4*>(src);
+            rawg[t4] = *reinterpret_cast<const uint4*>(src + p.ff_hidden);
           }
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // previous stores have read the boxes
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + bhalf) : "memory");   // previous stores have read the boxes
 #pragma unroll
-          for (int t8 = 0; t8 < 8; ++t8) {
-            const int r = quarter * 32 + t8 * 4 + (lane >> 3);
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int r = quarter * 32 + (part * 4 + t4) * 4 + (lane >> 3);
             const uint32_t off = swz128(r, lane & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(rawv[t8].x),
-                         "r"(rawv[t8].y), "r"(rawv[t8].z), "r"(rawv[t8].w) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(rawg[t8].x),
-                         "r"(rawg[t8].y), "r"(rawg[t8].z), "r"(rawg[t8].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(rawv[t4].x),
+                         "r"(rawv[t4].y), "r"(rawv[t4].z), "r"(rawv[t4].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(rawg[t4].x),
+                         "r"(rawg[t4].y), "r"(rawg[t4].z), "r"(rawg[t4].w) : "memory");
           }
-          __syncwarp();
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + bhalf) : "memory");   // both warps of a quarter filled it
 #pragma unroll
-          for (int c32 = 0; c32 < 2; ++c32) {
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + half * 128 + q * 64 + c32 * 32, v);
+          for (int c16 = 0; c16 < 2; ++c16) {
+            uint32_t v[16];
+            tmem_ld_32x16(taddr + bhalf * 128 + q * 64 + part * 32 + c16 * 16, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const int chunk = c32 * 4 + (i >> 3);
+            for (int i = 0; i < 16; i += 8) {
+              const int chunk = part * 4 + c16 * 2 + (i >> 3);
               const uint32_t off = swz128(row_in_tile, chunk);
               uint32_t wv[4], wg[4];
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -345,7 +366,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + bhalf) : "memory");
           if (issuer) {
             const int r0 = m_blk * kGemmBlockM;
             tma_store_2d(&tmC, stg, kq, r0);                        // du[:, k ..]        d value
@@ -420,7 +441,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     // outstanding TMA stores must have READ their staging smem before the CTA exits
     if (EPI == PEPI_FF_UP || EPI == PEPI_FF_BWD) {
-      if ((threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if ((threadIdx.x & 255) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if ((EPI != PEPI_STORE || p.use_tma_store) && threadIdx.x == 0) {
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }

@@ -311,6 +311,37 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, dt
 
 
+class PatchEmbedFn(torch.autograd.Function):
+    """tokens = patches @ W^T + bias + pos[index]  (x_clip.py:356-359, :382-383, with the
+    PatchDropout selection :134-151 already applied to `patches` and `index`).
+
+    patches bf16 [B*k, patch_dim] come from K.patchify_gather (only the kept patches are read from
+    the image); `index` int32 [B*k] is the patch index of every row = the row of the position table
+    the GEMM epilogue adds.  Backward: dW by the wgrad GEMM, d bias = column sums, d pos = rows of dy
+    scatter-added by `index`; the image needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, patches, index, weight, bias, table):
+        wb = weight_bf16(weight)
+        tbl16 = K.cast_bf16(table.detach())
+        y = K.gemm(patches, wb, bias=bias.detach(), residual=tbl16, res_row_idx=index)
+        ctx.save_for_backward(patches, index)
+        ctx.table_rows = table.shape[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        patches, index = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != BF16:
+            dy = dy.to(BF16)
+        dw = _wgrad(dy, patches)
+        db = K.colsum_rows_(torch.zeros(dy.shape[1], device=dy.device, dtype=F32), dy)
+        dt = K.scatter_add_rows_(torch.zeros((ctx.table_rows, dy.shape[1]), device=dy.device, dtype=F32),
+                                 dy, idx=index)
+        return None, None, dw, db, dt
+
+
 class ProjectL2NormFn(torch.autograd.Function):
     """z = normalize(e @ W^T) (x_clip.py:713-715).  Returns (z fp32, zrow, zcol): the last two
     are the split-bf16 MMA operands of the logits contraction (no grad), see xclip_l2norm_fwd."""

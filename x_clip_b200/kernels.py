@@ -93,7 +93,8 @@ def _rows2d(t: torch.Tensor, name: str) -> None:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0,
          out: Optional[torch.Tensor] = None, out_dtype=BF16, alpha: float = 1.0,
          bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         res_row_mod: int = 0, accumulate: bool = False) -> torch.Tensor:
+         res_row_mod: int = 0, res_row_idx: Optional[torch.Tensor] = None,
+         accumulate: bool = False) -> torch.Tensor:
     """out[M,N] (+)= alpha * A @ B^T (+bias) (+residual).  See xclip_gemm_bf16."""
     _need(a, BF16, "a"); _need(b, BF16, "b")
     _rows2d(a, "a"); _rows2d(b, "b")
@@ -123,11 +124,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
     if residual is not None:
         _need(residual, BF16, "residual"); _rows2d(residual, "residual")
         ldr = residual.stride(0)
+    if res_row_idx is not None:
+        if res_row_idx.dtype != torch.int32 or res_row_idx.numel() != M or not res_row_idx.is_contiguous() \
+                or res_row_idx.device != a.device:
+            raise _lib.XClipB200Error("gemm: res_row_idx must be a contiguous int32 [M] on the operands' device")
     fam = "gemm_wgrad" if (a_major == 1 and b_major == 1) else ("gemm_dgrad" if b_major == 1 else "gemm_fwd")
     nbytes = 2.0 * (M * K + N * K) + M * N * out.element_size() + (M * N * 2 if residual is not None else 0)
     _call(a, fam, 2.0 * M * N * K, nbytes, "xclip_gemm_bf16", a.data_ptr(), a.stride(0), a_major, b.data_ptr(), b.stride(0),
               b_major, out.data_ptr(), out.stride(0), 1 if out.dtype == F32 else 0, M, N, K,
-              float(alpha), _ptr(bias), _ptr(residual), ldr, int(res_row_mod),
+              float(alpha), _ptr(bias), _ptr(residual), ldr, int(res_row_mod), _ptr(res_row_idx),
               1 if accumulate else 0)
     return out
 
@@ -244,6 +249,41 @@ def attn_bwd(qkv, key_mask, o, d_o, lse, B, n, heads, scale, causal=False):
               dqkv.data_ptr(), dqkv.stride(0), _ptr(ws), B, n, heads, float(scale),
               1 if causal else 0)
     return dqkv
+
+
+def patchify_gather(img, patch, keep=None):
+    """img f32 [B,C,H,W] -> bf16 [B*k, patch*patch*C] (reference (p1 p2 c) order) for the patches
+    keep[b, j] (int64 [B,k]) or all patches in order."""
+    _need(img, F32, "image")
+    img = img.contiguous()
+    B, C, H, W = img.shape
+    n = (H // patch) * (W // patch)
+    k = n if keep is None else keep.shape[1]
+    if keep is not None:
+        if keep.dtype != torch.int64 or keep.shape[0] != B or keep.device != img.device:
+            raise _lib.XClipB200Error("patchify: keep must be int64 [B, k] on the image's device")
+        keep = keep.contiguous()
+    out = torch.empty((B * k, patch * patch * C), device=img.device, dtype=BF16)
+    _call(img, "embed", 0.0, B * k * patch * patch * C * 6.0, "xclip_patchify_gather", img.data_ptr(), B, C, H, W,
+          int(patch), _ptr(keep), k, out.data_ptr())
+    return out
+
+
+def scatter_add_rows_(dst, src, idx=None, period=0):
+    """dst f32 [V,d] rows idx[r] (int32) or r % period += src bf16 [rows,d]."""
+    _need(src, BF16, "src"); _rows2d(src, "src"); _need(dst, F32, "dst")
+    rows, d = src.shape
+    _call(src, "embed", 0.0, rows * d * 6.0, "xclip_scatter_add_rows", _ptr(idx), int(period), src.data_ptr(),
+          src.stride(0), dst.data_ptr(), rows, d, dst.shape[0])
+    return dst
+
+
+def colsum_rows_(dst, src):
+    """dst f32 [d] += column sums of src bf16 [rows,d]."""
+    _need(src, BF16, "src"); _rows2d(src, "src"); _need(dst, F32, "dst")
+    _call(src, "embed", 0.0, src.numel() * 2.0, "xclip_colsum_rows", src.data_ptr(), src.stride(0), dst.data_ptr(),
+          src.shape[0], src.shape[1])
+    return dst
 
 
 def ff_weights(w1, w2, g4):
