@@ -278,6 +278,36 @@ def clip_forward(p: Params, text: Tensor, image: Tensor, cfg: ClipConfig,
     return loss
 
 
+def clip_forward_multiview(p: Params, texts: Sequence[Tensor], images: Sequence[Tensor],
+                           cfg: ClipConfig, multiview_loss_weight: float = 0.1) -> Tensor:
+    """CLIP.forward(text, image, aug_text=..., aug_image=..., return_loss=True) (:623-650, :750-755,
+    :851-868): texts[0] / images[0] are the originals, the others augmented views of the SAME pairs.
+    Every (text view m, image view n) combination is an InfoNCE problem of its own; the loss is
+    (1 - w) * loss[0,0] + w * mean(the other m*n - 1 losses)."""
+    assert not cfg.use_all_token_embeds
+    zs_t, zs_i = [], []
+    for t in texts:
+        m = t != cfg.text_pad_id
+        et = encode_text(t, m, p, cfg)
+        if cfg.text_causal_mask:
+            et = eos_to_front(et, t, cfg.text_eos_id)
+        te = et[:, 0]
+        zt = unit_rows(te @ p["to_text_latent.weight"].t())
+        ztx = unit_rows(te @ p["to_text_latent_extra.weight"].t()) if cfg.extra_latent_projection else zt
+        zs_t.append((zt, ztx))
+    for im in images:
+        ie = encode_image(im, p, cfg)[:, 0]
+        zi = unit_rows(ie @ p["to_visual_latent.weight"].t())
+        zix = unit_rows(ie @ p["to_visual_latent_extra.weight"].t()) if cfg.extra_latent_projection else zi
+        zs_i.append((zi, zix))
+    losses = [contrastive_loss(zt, zi, ztx, zix, p["temperature"], cfg)
+              for (zt, ztx) in zs_t for (zi, zix) in zs_i]
+    if len(losses) == 1:
+        return losses[0]
+    w = multiview_loss_weight
+    return losses[0] * (1 - w) + torch.stack(losses[1:]).mean() * w
+
+
 def clip_forward_sharded(p: Params, texts: Sequence[Tensor], images: Sequence[Tensor],
                          cfg: ClipConfig, rank: int) -> Tensor:
     """What rank `rank` of a W-rank job computes (x_clip/distributed.py:41-56 +

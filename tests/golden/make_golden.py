@@ -155,6 +155,33 @@ def run_case(x_clip, name, cfg_kwargs, batch, pad_fraction, patch_dropout):
     return out
 
 
+def multiview_case(x_clip, name, cfg_kwargs, batch, n_aug_text, n_aug_image):
+    """aug_text / aug_image views through the reference (x_clip.py:623-650, :851-868) vs the oracle."""
+    cfg = O.ClipConfig(**cfg_kwargs)
+    state = O.protocol_state_dict(cfg, WEIGHT_SEED)
+    views = [O.protocol_inputs(cfg, batch, INPUT_SEED + 17 * v, 0.2) for v in range(1 + max(n_aug_text, n_aug_image))]
+    texts = [views[v][0] for v in range(1 + n_aug_text)]
+    images = [views[v][1] for v in range(1 + n_aug_image)]
+    clip = build_reference(x_clip, cfg_kwargs, 0.0, state)
+    loss = clip(texts[0], images[0], return_loss=True,
+                aug_text=tuple(texts[1:]) if n_aug_text else None,
+                aug_image=tuple(images[1:]) if n_aug_image else None)
+    loss.backward()
+    grads = {k: p.grad for k, p in clip.named_parameters() if p.grad is not None}
+    p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    o_loss = O.clip_forward_multiview(p, texts, images, cfg, clip.multiview_loss_weight)
+    o_loss.backward()
+    assert abs(o_loss.item() - loss.item()) <= 3e-6 * max(1.0, abs(loss.item())), (name, o_loss.item(), loss.item())
+    for k, g in grads.items():
+        assert (p[k].grad - g).norm().item() / (g.norm().item() + 1e-12) < 2e-4, (name, k)
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+    return dict(case=name, cfg=cfg_kwargs, batch=batch, n_aug_text=n_aug_text, n_aug_image=n_aug_image,
+                view_seed_stride=17, pad_fraction=0.2, weight_seed=WEIGHT_SEED, input_seed=INPUT_SEED,
+                multiview_loss_weight=clip.multiview_loss_weight, loss=loss.item(),
+                dtemperature=grads["temperature"].item(), grad_norm=total,
+                grad_norms={k: g.double().norm().item() for k, g in grads.items()})
+
+
 def survey_anchor(x_clip, **extra):
     """SURVEY.md 4 protocol: manual_seed(0) -> CLIP(README cfg) -> manual_seed(1) -> inputs."""
     torch.manual_seed(0)
@@ -239,6 +266,12 @@ def main():
     x_clip = import_reference()
     for name, (cfgk, batch, padf, drop) in CASES.items():
         out = run_case(x_clip, name, cfgk, batch, padf, drop)
+        (HERE / f"{name}.json").write_text(json.dumps(out))
+        print(f"{name}: loss={out['loss']:.7f} grad_norm={out['grad_norm']:.6f} dtemp={out['dtemperature']:.7f}")
+    for name, cfgk, na_t, na_i in (("tiny_multiview", dict(TINY), 1, 2),
+                                   ("tiny_multiview_dcl_extra", dict(TINY, decoupled_contrastive_learning=True,
+                                                                     extra_latent_projection=True), 2, 0)):
+        out = multiview_case(x_clip, name, cfgk, 5, na_t, na_i)
         (HERE / f"{name}.json").write_text(json.dumps(out))
         print(f"{name}: loss={out['loss']:.7f} grad_norm={out['grad_norm']:.6f} dtemp={out['dtemperature']:.7f}")
     anchors = [survey_anchor(x_clip),

@@ -9,8 +9,8 @@ done by the CUDA kernels behind include/xclip_b200.h, scheduled by x_clip_b200.e
 Feature combinations the kernels do not cover raise at construction (never a silent CPU or
 eager fallback): dim_head != 64, model dims not multiples of 256, a causal text tower longer than
 128 tokens, rotary + causal together (broken in the reference itself: n+1 angles for n tokens,
-x_clip.py:328), dropout > 0, MLM / visual SSL / multiview / similarity-regularisation terms and
-conv-downsampled image latents.
+x_clip.py:328), dropout > 0, the similarity-regularisation term and conv-downsampled image
+latents.  MLM, SimSiam / SimCLR and the multiview term run through the fast encoders (aux.py).
 """
 from __future__ import annotations
 
@@ -315,9 +315,6 @@ class CLIP(nn.Module):
             'CLS token must be included on both vision and text transformers if you are not using fine-grained contrastive learning loss'
         assert not (text_causal_mask and text_eos_id is None), \
             'text EOS token id must be given if using causal mask in text transformer'
-        _require(not use_mlm, "use_mlm (MLM auxiliary loss) is outside the accelerated hot path")
-        _require(not (use_visual_ssl or visual_ssl is not None),
-                 "visual SSL (SimSiam/SimCLR) is outside the accelerated hot path")
         _require(not downsample_image_embeds, "downsample_image_embeds is not implemented")
         _require(sim_reg_loss_weight == 0., "sim_reg_loss_weight > 0 is not implemented")
         _require(dim_latent % 256 == 0 and dim_latent <= 1024, "dim_latent must be 256/512/768/1024")
@@ -338,7 +335,7 @@ class CLIP(nn.Module):
             self.text_transformer = text_encoder
         else:
             self.text_transformer = TextTransformer(
-                dim=dim_text, num_tokens=num_text_tokens, max_seq_len=text_seq_len,
+                dim=dim_text, num_tokens=num_text_tokens + (1 if use_mlm else 0), max_seq_len=text_seq_len,
                 depth=text_enc_depth, heads=text_heads, causal=text_causal_mask,
                 dim_head=text_dim_head, rotary_pos_emb=text_rotary_pos_emb,
                 checkpoint_during_training=checkpoint_during_training)
@@ -352,10 +349,28 @@ class CLIP(nn.Module):
                 dim_head=visual_dim_head, patch_dropout=visual_patch_dropout,
                 checkpoint_during_training=checkpoint_during_training)
 
-        self.use_mlm = False
-        self.use_visual_ssl = False
-        self.text_ssl_loss_weight = 0
-        self.image_ssl_loss_weight = 0
+        # auxiliary self-supervised losses through the fast encoders (reference :516-552; aux.py)
+        self.use_mlm = use_mlm
+        self.text_ssl_loss_weight = text_ssl_loss_weight if use_mlm else 0
+        if use_mlm:
+            from .aux import MLM
+            mlm_kwargs = {k[len('mlm_'):]: kwargs.pop(k) for k in list(kwargs) if k.startswith('mlm_')}
+            self.mlm = MLM(self.text_transformer, dim=dim_text, num_tokens=num_text_tokens, **mlm_kwargs)
+        self.use_visual_ssl = use_visual_ssl or visual_ssl is not None
+        self.image_ssl_loss_weight = image_ssl_loss_weight if use_visual_ssl else 0     # (sic, :536)
+        if self.use_visual_ssl:
+            if visual_ssl is not None:
+                self.visual_ssl = visual_ssl
+            else:
+                from .aux import SimCLR, SimSiam
+                if visual_ssl_type == 'simsiam':
+                    self.visual_ssl = SimSiam(self.visual_transformer, image_size=visual_image_size,
+                                              channels=channels, rep_dim=dim_image)
+                elif visual_ssl_type == 'simclr':
+                    self.visual_ssl = SimCLR(self.visual_transformer, image_size=visual_image_size,
+                                             channels=channels, rep_dim=dim_image, temperature=simclr_temperature)
+                else:
+                    raise ValueError('unknown visual_ssl_type')
 
         self.to_text_latent = nn.Linear(dim_text, dim_latent, bias=False)
         self.to_visual_latent = nn.Linear(dim_image, dim_latent, bias=False)
@@ -430,12 +445,39 @@ class CLIP(nn.Module):
         aug_text=None,
         aug_image=None,
     ):
-        _require(aug_text is None and aug_image is None, "multiview (aug_text/aug_image) is not implemented")
-        assert not (return_loss and not self.training), 'loss cannot be used if not training'
         _require(text.is_cuda and image.is_cuda, "inputs must live on a CUDA (sm_100) device")
 
         text_mask = text != self.text_pad_id
-        if (return_loss and self.microbatch and text.shape[0] > self.microbatch
+
+        # auxiliary losses on the un-augmented batch (reference :616-621)
+        text_ssl_loss = image_ssl_loss = 0
+        if return_loss:
+            text_ssl_loss = self.mlm(text, mask=text_mask) if self.use_mlm else 0
+            image_ssl_loss = self.visual_ssl(image) if self.use_visual_ssl else 0
+
+        # multiview: augmented texts / images are further "views" of the same pairs (:625-650)
+        num_batch_texts = num_batch_images = 1
+        if aug_text is not None:
+            aug_text = aug_text if isinstance(aug_text, (tuple, list)) else (aug_text,)
+            assert all(t.shape == text.shape for t in aug_text)
+            num_batch_texts = len(aug_text) + 1
+            text = torch.cat((text, *aug_text), dim=0)
+            text_mask = text != self.text_pad_id
+        if aug_image is not None:
+            aug_image = aug_image if isinstance(aug_image, (tuple, list)) else (aug_image,)
+            assert all(i.shape == image.shape for i in aug_image)
+            num_batch_images = len(aug_image) + 1
+            image = torch.cat((image, *aug_image), dim=0)
+        is_multiview = num_batch_texts > 1 or num_batch_images > 1
+        assert not (return_loss and not self.training), 'loss cannot be used if not training'
+        assert not (not return_loss and is_multiview), 'do not pass in augmented texts or images if not training'
+        assert not (self.multiview_loss_weight == 0 and is_multiview), \
+            'multiview loss weight cannot be 0 if augmented text or images passed in'
+        _require(not (is_multiview and self.use_all_token_embeds),
+                 "multiview with use_all_token_embeds is not implemented")
+
+        has_aux = is_multiview or self.use_mlm or self.use_visual_ssl
+        if (return_loss and self.microbatch and text.shape[0] > self.microbatch and not has_aux
                 and not self.use_all_token_embeds and not (freeze_image_encoder or freeze_text_encoder)):
             return E.ChunkedClipLossFn.apply(self, text, image, text_mask, int(self.microbatch),
                                              self.temperature)
@@ -482,7 +524,29 @@ class CLIP(nn.Module):
             from .filip import filip_loss
             return filip_loss(self, zt, zi, zt_x, zi_x, ops, text_mask)
 
-        return E.ContrastiveLossFn.apply(
-            zt, zi, zt_x if self.extra_latent_projection else None,
-            zi_x if self.extra_latent_projection else None, self.temperature,
-            tuple(ops), self.decoupled_contrastive_learning, self.requires_all_gather)
+        def cl(tsl, isl):
+            """contrastive loss of text view rows `tsl` against image view rows `isl`"""
+            o = [(ops[0][0][tsl], ops[0][1][tsl]), (ops[1][0][isl], ops[1][1][isl])]
+            if self.extra_latent_projection:
+                o += [(ops[2][0][tsl], ops[2][1][tsl]), (ops[3][0][isl], ops[3][1][isl])]
+            return E.ContrastiveLossFn.apply(
+                zt[tsl], zi[isl], zt_x[tsl] if self.extra_latent_projection else None,
+                zi_x[isl] if self.extra_latent_projection else None, self.temperature,
+                tuple(o), self.decoupled_contrastive_learning, self.requires_all_gather)
+
+        if not has_aux:
+            return cl(slice(None), slice(None))
+
+        # every (text view m, image view n) pair is its own InfoNCE problem; [0] is the main loss,
+        # the others are averaged into the multiview term (reference :750-755, :851-868)
+        b = text.shape[0] // num_batch_texts
+        losses = [cl(slice(m * b, (m + 1) * b), slice(n * b, (n + 1) * b))
+                  for m in range(num_batch_texts) for n in range(num_batch_images)]
+        cl_loss = losses[0]
+        multiview_w = self.multiview_loss_weight if is_multiview else 0
+        cl_w = 1 - (self.text_ssl_loss_weight + self.image_ssl_loss_weight + multiview_w)
+        loss = cl_loss * cl_w + text_ssl_loss * self.text_ssl_loss_weight \
+            + image_ssl_loss * self.image_ssl_loss_weight
+        if is_multiview:
+            loss = loss + torch.stack(losses[1:]).mean() * multiview_w
+        return loss

@@ -239,9 +239,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int bs = sub >> 1;                                      // box set
         const uint32_t stg = smem_u32(smem_c) + bs * 3 * S::kBox;     // value | gate | hp boxes
         const bool issuer = (threadIdx.x == bs * 256);
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
+        // All arithmetic happens BEFORE the staging boxes are touched: the results wait in registers
+        // (48 packed words) while the previous tile's TMA stores are still draining the boxes, so the
+        // store latency overlaps the TMEM reads and the GELU math instead of serialising with them.
         float s1 = 0.f, s2 = 0.f;
+        uint32_t pv[16], pg[16], ph[16];
 #pragma unroll
         for (int c16 = 0; c16 < 2; ++c16) {
           uint32_t vv[16], gg[16];
@@ -249,27 +251,40 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_32x16(taddr + 128 + sub * 32 + c16 * 16, gg);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; i += 8) {
-            float va[8], ga[8], hp[8];
+          for (int i = 0; i < 16; i += 2) {
+            float hp2[2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              va[e] = __uint_as_float(vv[i + e]);
-              ga[e] = __uint_as_float(gg[i + e]);
-              hp[e] = bf16_rn(va[e] * gelu_erf(ga[e]));   // statistics of what the next GEMM reads
-              s1 += hp[e];
-              s2 = fmaf(hp[e], hp[e], s2);
+            for (int e = 0; e < 2; ++e) {
+              const float va = __uint_as_float(vv[i + e]), ga = __uint_as_float(gg[i + e]);
+              hp2[e] = bf16_rn(va * gelu_erf(ga));        // statistics of what the next GEMM reads
+              s1 += hp2[e];
+              s2 = fmaf(hp2[e], hp2[e], s2);
             }
-            const int chunk = (sub & 1) * 4 + c16 * 2 + (i >> 3);
-            st_box_bf16x8(stg, row_in_tile, chunk, va);
-            st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, ga);
-            st_box_bf16x8(stg + 2 * S::kBox, row_in_tile, chunk, hp);
+            pv[c16 * 8 + (i >> 1)] = pack_bf16x2(__uint_as_float(vv[i]), __uint_as_float(vv[i + 1]));
+            pg[c16 * 8 + (i >> 1)] = pack_bf16x2(__uint_as_float(gg[i]), __uint_as_float(gg[i + 1]));
+            ph[c16 * 8 + (i >> 1)] = pack_bf16x2(hp2[0], hp2[1]);
           }
+        }
+        // the accumulator is in registers now: hand the TMEM buffer back to the MMA warp at once
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = swz128(row_in_tile, (sub & 1) * 4 + c);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(pv[4 * c]),
+                       "r"(pv[4 * c + 1]), "r"(pv[4 * c + 2]), "r"(pv[4 * c + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(pg[4 * c]),
+                       "r"(pg[4 * c + 1]), "r"(pg[4 * c + 2]), "r"(pg[4 * c + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + 2 * S::kBox + off), "r"(ph[4 * c]),
+                       "r"(ph[4 * c + 1]), "r"(ph[4 * c + 2]), "r"(ph[4 * c + 3]) : "memory");
         }
         // the two warps sharing a row of this box set combine their partial sums (one red pair per
         // row, box set and tile instead of two)
         float2* xch = reinterpret_cast<float2*>(smem_c + S::kStagingBytes + S::kBarrierBytes) + bs * 128;
         if (sub & 1) xch[row_in_tile] = make_float2(s1, s2);
-        tcgen05_fence_before();
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
         if (!(sub & 1)) {
@@ -435,9 +450,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if constexpr (EPI != PEPI_FF_UP) {     // (FF_UP released its accumulator before staging)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      }
     }
     // outstanding TMA stores must have READ their staging smem before the CTA exits
     if (EPI == PEPI_FF_UP || EPI == PEPI_FF_BWD) {
