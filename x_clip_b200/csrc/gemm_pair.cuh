@@ -53,10 +53,10 @@ struct PairCfg {
   static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBox = 128 * 128;                          // one [128 rows x 64 bf16] staging box
-  // STORE: 2 boxes (double buffered); FF_UP: (value, gate, hp) x 2 column halves; FF_DOWN: (out, acc)
-  // FF_BWD: (d value, d gate) x 2 column halves
-  static constexpr int kStagingBytes = (EPI == PEPI_FF_UP ? 6 : (EPI == PEPI_FF_BWD ? 4 : 2)) * kBox;
-  static constexpr int kStages = EPI == PEPI_FF_UP ? 4 : (EPI == PEPI_FF_BWD ? 5 : 6);
+  // STORE: 2 boxes (double buffered); FF_UP: one box per column half (value, gate and hp pass through it
+  // one after the other - they wait in registers); FF_DOWN: (out, acc); FF_BWD: (d value, d gate) x 2 halves
+  static constexpr int kStagingBytes = (EPI == PEPI_FF_BWD ? 4 : 2) * kBox;
+  static constexpr int kStages = EPI == PEPI_FF_BWD ? 5 : 6;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kScratchBytes = EPI == PEPI_FF_UP ? 2 * 128 * 8 : 0;   // row-sum exchange
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + kScratchBytes;
@@ -237,7 +237,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // of (value, gate, hp) boxes [128 rows x 64 columns].
         const int sub = warp >> 2;
         const int bs = sub >> 1;                                      // box set
-        const uint32_t stg = smem_u32(smem_c) + bs * 3 * S::kBox;     // value | gate | hp boxes
+        const uint32_t stg = smem_u32(smem_c) + bs * S::kBox;         // this column half's staging box
         const bool issuer = (threadIdx.x == bs * 256);
         // All arithmetic happens BEFORE the staging boxes are touched: the results wait in registers
         // (48 packed words) while the previous tile's TMA stores are still draining the boxes, so the
@@ -269,36 +269,37 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t off = swz128(row_in_tile, (sub & 1) * 4 + c);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(pv[4 * c]),
-                       "r"(pv[4 * c + 1]), "r"(pv[4 * c + 2]), "r"(pv[4 * c + 3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(pg[4 * c]),
-                       "r"(pg[4 * c + 1]), "r"(pg[4 * c + 2]), "r"(pg[4 * c + 3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + 2 * S::kBox + off), "r"(ph[4 * c]),
-                       "r"(ph[4 * c + 1]), "r"(ph[4 * c + 2]), "r"(ph[4 * c + 3]) : "memory");
-        }
         // the two warps sharing a row of this box set combine their partial sums (one red pair per
         // row, box set and tile instead of two)
         float2* xch = reinterpret_cast<float2*>(smem_c + S::kStagingBytes + S::kBarrierBytes) + bs * 128;
         if (sub & 1) xch[row_in_tile] = make_float2(s1, s2);
-        fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
+        // value, gate and hp pass through the single box one after the other
+        const int hcol = n_blk * 128 + bs * 64;               // hidden-unit column of this box
+        const int r0 = m_blk * kGemmBlockM;
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
+          const uint32_t* src = which == 0 ? pv : (which == 1 ? pg : ph);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = swz128(row_in_tile, (sub & 1) * 4 + c);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(src[4 * c]),
+                         "r"(src[4 * c + 1]), "r"(src[4 * c + 2]), "r"(src[4 * c + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
+          if (issuer) {
+            if (which == 0) tma_store_2d(&tmC, stg, hcol, r0);                      // u[:, hcol ..]       value
+            else if (which == 1) tma_store_2d(&tmC, stg, p.ff_hidden + hcol, r0);   // u[:, 4d + hcol ..]  gate
+            else tma_store_2d(&tmC2, stg, hcol, r0);                                // hp[:, hcol ..]
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
         if (!(sub & 1)) {
           const float2 o = xch[row_in_tile];
           s1 += o.x;
           s2 += o.y;
-        }
-        if (issuer) {
-          const int hcol = n_blk * 128 + bs * 64;               // hidden-unit column of this box
-          const int r0 = m_blk * kGemmBlockM;
-          tma_store_2d(&tmC, stg, hcol, r0);                    // u[:, hcol ..]            value
-          tma_store_2d(&tmC, stg + S::kBox, p.ff_hidden + hcol, r0);   // u[:, 4d + hcol ..]  gate
-          tma_store_2d(&tmC2, stg + 2 * S::kBox, hcol, r0);     // hp[:, hcol ..]
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (row_ok && !(sub & 1)) {
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row), "f"(s1) : "memory");
