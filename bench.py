@@ -524,6 +524,23 @@ def main():
         del slots
         note("e2e timing done")
 
+    # ---- (2b) N > 1: the same step with the weight-gradient all-reduce inside (GradSync buckets
+    #           overlapped with backward; the reference leaves this to the user's DDP wrapper)
+    with_sync = None
+    if world > 1 and not args.grad_sync:
+        from x_clip_b200.distributed import GradSync
+        run.grad_sync = GradSync(run.clip)
+        n_sync = max(2, min(args.steps, 3))
+        ms_sync, _ = run.timed(n_sync, 1)
+        run.grad_sync.remove()
+        run.grad_sync = None
+        nbytes = sum(p.numel() * 4 for p in run.params if p.requires_grad)
+        with_sync = {"pairs_per_s": round(B * world * n_sync / (ms_sync / 1e3), 2),
+                     "ms_per_step": round(ms_sync / n_sync, 3), "steps": n_sync,
+                     "allreduced_bytes_per_step": nbytes,
+                     "what": "x_clip_b200.distributed.GradSync: fp32 bucketed all-reduce launched from inside backward"}
+        note(f"with grad sync: {with_sync}")
+
     # ---- (3) instrumented step for the roofline (every rank runs it - it contains collectives)
     prof = None
     if not args.no_profile:
@@ -661,6 +678,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "gpu_eager_baseline": eager,
         "multirank_parity": parity,
+        "with_grad_sync": with_sync,
         "other_workloads": extras,
         "kernel_families": families,
     }

@@ -83,7 +83,7 @@ ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int warp_stride = gridDim.x * kRowWarps;
-  constexpr bool kPipelined = NV <= 2;
+  constexpr bool kPipelined = NV <= 3;   // next row's vectors in flight while this row is reduced
   uint4 nx[NV];
   if (kPipelined && warp_global < rows) {
 #pragma unroll
@@ -201,9 +201,25 @@ ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restric
       nrstd = stats[2 * (long long)r + 1];
     }
   };
+  // wide rows (no register pipeline): pull the next row towards L2 instead - no registers held,
+  // the just-in-time loads then see L2 instead of HBM latency
+  auto prefetch_l2 = [&](long long r) {
+    if (r < rows && (lane & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int col = (j * 32 + lane) * 8;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + r * ldx + col));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + r * lddy + col));
+        if (add != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(add + r * ldadd + col));
+      }
+    }
+  };
   if (kPipelined) prefetch(warp_global);
   for (int row = warp_global; row < rows; row += warp_stride) {
-    if (!kPipelined) prefetch(row);
+    if (!kPipelined) {
+      prefetch_l2((long long)row + warp_stride);
+      prefetch(row);
+    }
     const float mean = nmean, rstd = nrstd;
     float xh[NV][8], gd[NV][8];
     uint4 ca[NV];
@@ -808,7 +824,7 @@ extern "C" int xclip_ff_w2_grad_post(float* raw, const float* vsum, const float*
   if (rc) return rc;
   XCLIP_REQUIRE(raw && vsum && g && d > 0 && d % 256 == 0, "ff_w2_grad_post: bad arguments");
   XCLIP_REQUIRE((dg == nullptr) == (w2 == nullptr), "ff_w2_grad_post: dg and w2 go together");
-  const int rows_per_block = 64;
+  const int rows_per_block = 8;      // 4d/256 x d/8 blocks: enough loads in flight for a 28 MB pass
   dim3 grid((4 * d + 255) / 256, (d + rows_per_block - 1) / rows_per_block);
   ff_w2_grad_post_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(raw, vsum, g, w2, dg, d,
                                                                                  rows_per_block);
