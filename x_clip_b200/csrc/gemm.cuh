@@ -289,7 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 4 && XCLIP_ONE_LANE(lane)) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.use_tma_store) tma_prefetch_desc(&tmC);
+    if (p.use_tma_store || EPI == EPI_NCE_BWD) tma_prefetch_desc(&tmC);
   }
   if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
   tcgen05_fence_before();
@@ -480,13 +480,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int diag_col = row + p.diag_offset;
         const float lr2 = (row_ok && p.lse_row) ? p.lse_row[row] * 1.4426950408889634f : 0.f;
         float tsum = 0.f;
+        // g leaves through swizzled 64-column boxes in shared memory and TMA stores (full 128-byte
+        // lines; per-thread 16-byte row stores made this epilogue LSU-bound: 0.21 of the bf16 peak)
+        const int row_in_tile = warp * 32 + lane;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = n_blk * BLOCK_N + c * 32;
-          if (row_ok && col0 < p.N) {
+        for (int q = 0; q < BLOCK_N / 64; ++q) {
+          const uint32_t stg = smem_u32(smem_c) + (store_count & 1) * 16384;
+          if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int c32 = 0; c32 < 2; ++c32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + q * 64 + c32 * 32, v);
+            tmem_ld_wait();
+            const int col0 = n_blk * BLOCK_N + q * 64 + c32 * 32;
             float gq[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -494,30 +501,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float acc_v = __uint_as_float(v[i]);
               const bool is_diag = (col == diag_col);
               float gv = 0.f;
-              if (col < p.N) {
+              if (row_ok && col < p.N) {
                 if (!(p.dcl && is_diag)) {
                   if (p.w_row != 0.f) gv += w_row * exp2f(acc_v * a2 - lr2);
                   if (p.w_col != 0.f)
-                    gv += w_col * exp2f(acc_v * a2 - p.lse_col[col] * 1.4426950408889634f);
+                    gv += w_col * exp2f(acc_v * a2 - __ldg(p.lse_col + col) * 1.4426950408889634f);
                 }
                 if (is_diag) gv -= w_diag;
                 tsum += gv * acc_v * alpha;
               }
-              gq[i] = gv * alpha;   // temperature folded in: d rows = gq @ cols
+              gq[i] = gv * alpha;   // temperature folded in: d rows = gq @ cols; 0 beyond N / M
             }
-            bf16* crow = reinterpret_cast<bf16*>(p.c) + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {
-                uint4 o;
-                o.x = pack_bf16x2(gq[i], gq[i + 1]);
-                o.y = pack_bf16x2(gq[i + 2], gq[i + 3]);
-                o.z = pack_bf16x2(gq[i + 4], gq[i + 5]);
-                o.w = pack_bf16x2(gq[i + 6], gq[i + 7]);
-                *reinterpret_cast<uint4*>(crow + i) = o;
-              }
+            for (int i = 0; i < 4; ++i) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                               stg + swz128(row_in_tile, c32 * 4 + i)),
+                           "r"(pack_bf16x2(gq[i * 8 + 0], gq[i * 8 + 1])),
+                           "r"(pack_bf16x2(gq[i * 8 + 2], gq[i * 8 + 3])),
+                           "r"(pack_bf16x2(gq[i * 8 + 4], gq[i * 8 + 5])),
+                           "r"(pack_bf16x2(gq[i * 8 + 6], gq[i * 8 + 7]))
+                           : "memory");
             }
           }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 0) {
+            const int c0 = n_blk * BLOCK_N + q * 64;
+            if (c0 < (int)p.ldc) {      // the map spans ldc = roundup8(N) columns: the pad columns get zeros
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmC)),
+                  "r"(stg), "r"(c0), "r"(m_blk * kGemmBlockM)
+                  : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++store_count;
         }
         if (p.dtemp != nullptr) {
           tsum = warp_sum(tsum);
@@ -528,7 +547,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (EPI == EPI_STORE && p.use_tma_store && threadIdx.x == 0)
+    if (((EPI == EPI_STORE && p.use_tma_store) || EPI == EPI_NCE_BWD) && threadIdx.x == 0)
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
