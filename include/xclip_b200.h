@@ -195,6 +195,7 @@ int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float*
  *   ff_up           : u = [value | gate] bf16 [M, 8d] (reference layout, kept for the backward),
  *                     hp = value * gelu_erf(gate) bf16 [M, 4d], rowsum[r] += (sum hp, sum hp^2)
  *                     (rowsum f32 [M, 2], zeroed by the caller) - one GEMM, GEGLU in its epilogue.
+ *                     u may be NULL (forward-only sweeps: two thirds of the output traffic saved).
  *   ff_down         : out = rstd_r * (hp w2g^T - mean_r * colvec) + residual  (== LN(hp) g W2^T + x1),
  *                     acc_out = bf16(hp w2g^T), stats[r] = (mean, rstd) - one GEMM.
  *   ff_bwd_prep     : dxs = bf16(dx * rstd_r) [M, d]; vsum[j] += sum_r dxs[r,j] * mean_r; with acc and

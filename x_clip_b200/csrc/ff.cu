@@ -116,7 +116,9 @@ extern "C" int xclip_ff_up(const void* x, int64_t ldx, const void* w1p, void* u,
                            int64_t ldhp, float* rowsum, int M, int d, xclip_stream_t stream) {
   int rc = xclip_init();
   if (rc) return rc;
-  XCLIP_REQUIRE(x && w1p && u && hp && rowsum, "ff_up: null pointer");
+  XCLIP_REQUIRE(x && w1p && hp && rowsum, "ff_up: null pointer");
+  const bool skip_u = (u == nullptr);      // forward-only sweeps: hp is all the down-projection needs
+  if (skip_u) { u = hp; ldu = ldhp >= 8 * (int64_t)d ? ldhp : 8 * (int64_t)d; }   // (placeholder map, never stored to)
   XCLIP_REQUIRE(M > 0 && d > 0 && d % 256 == 0, "ff_up: M=%d d=%d (d %% 256)", M, d);
   XCLIP_REQUIRE(ldx % 8 == 0 && ldx >= d && ldu % 8 == 0 && ldu >= 8 * d && ldhp % 8 == 0 && ldhp >= 4 * d,
                 "ff_up: bad leading dimensions");
@@ -124,11 +126,13 @@ extern "C" int xclip_ff_up(const void* x, int64_t ldx, const void* w1p, void* u,
   CUtensorMap tmA, tmB, tmC, tmC2;
   if ((rc = encode_2d_bf16(&tmA, x, (uint64_t)d, (uint64_t)M, (uint64_t)ldx, 64, kGemmBlockM))) return rc;
   if ((rc = encode_2d_bf16(&tmB, w1p, (uint64_t)d, (uint64_t)(8 * d), (uint64_t)d, 64, 128))) return rc;
-  if ((rc = encode_2d_bf16(&tmC, u, (uint64_t)(8 * d), (uint64_t)M, (uint64_t)ldu, 64, kGemmBlockM))) return rc;
+  if (skip_u) {
+    if ((rc = encode_2d_bf16(&tmC, hp, (uint64_t)(4 * d), (uint64_t)M, (uint64_t)ldhp, 64, kGemmBlockM))) return rc;
+  } else if ((rc = encode_2d_bf16(&tmC, u, (uint64_t)(8 * d), (uint64_t)M, (uint64_t)ldu, 64, kGemmBlockM))) return rc;
   if ((rc = encode_2d_bf16(&tmC2, hp, (uint64_t)(4 * d), (uint64_t)M, (uint64_t)ldhp, 64, kGemmBlockM))) return rc;
   GemmParams p = {};
   p.M = M; p.N = 8 * d; p.K = d; p.split_k = 1; p.alpha = 1.f;
-  p.ff_rowsum = rowsum; p.ff_hidden = 4 * d;
+  p.ff_rowsum = rowsum; p.ff_hidden = 4 * d; p.ff_skip_u = skip_u ? 1 : 0;
   return launch_pair_ff<PEPI_FF_UP>(tmA, tmB, tmC, tmC2, p, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -64,6 +64,7 @@ struct GemmParams {
   float* ff_stats;         // DOWN: [M,2] (mean, rstd) of the GEGLU output rows, written for the backward
   float ff_eps;            // LayerNorm epsilon
   int ff_hidden;           // 4*dim: LayerNorm width; column offset of the gate half inside u
+  int ff_skip_u;           // UP: do not write u = [value | gate] (inference / no-grad sweeps need only hp)
   const bf16* ff_u;        // BWD: saved [value | gate] activations [M, 8d]
   long long ff_ldu;
   const float* ff_ab;      // BWD: [M,2] per-row (mean_k(gdh), mean_k(gdh * hn)) from xclip_ff_bwd_prep
@@ -88,6 +89,12 @@ struct GemmSmem {
   static constexpr int kStagingBytes = 2 * 128 * 128;  // two [128 rows x 64 bf16] output boxes
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes;
 };
+
+__device__ __forceinline__ float nce_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Epilogue of one 128 x BLOCK_N accumulator tile (EPI_STORE): C = alpha*acc (+bias) (+residual) as
 // bf16 through swizzled smem staging + TMA stores, or fp32 direct / atomic.  Called by the four
@@ -495,6 +502,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_wait();
             const int col0 = n_blk * BLOCK_N + q * 64 + c32 * 32;
             float gq[32];
+            // interior chunk (all 32 columns exist, the positive is elsewhere): ~10 instructions per
+            // element, two ex2.approx each; the general path keeps the per-element predicates
+            const bool interior = row_ok && col0 + 32 <= p.N && (diag_col < col0 || diag_col >= col0 + 32);
+            if (interior) {
+              float part = 0.f;
+              if (p.w_col != 0.f) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 lc = __ldg(reinterpret_cast<const float4*>(p.lse_col + col0 + i));
+                  const float l4[4] = {lc.x, lc.y, lc.z, lc.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float acc_v = __uint_as_float(v[i + e]);
+                    const float x = acc_v * a2;
+                    float gv = w_col * nce_ex2(fmaf(l4[e], -1.4426950408889634f, x));
+                    if (p.w_row != 0.f) gv = fmaf(w_row, nce_ex2(x - lr2), gv);
+                    part = fmaf(gv, acc_v, part);
+                    gq[i + e] = gv * alpha;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float acc_v = __uint_as_float(v[i]);
+                  const float gv = w_row * nce_ex2(fmaf(acc_v, a2, -lr2));
+                  part = fmaf(gv, acc_v, part);
+                  gq[i] = gv * alpha;
+                }
+              }
+              tsum = fmaf(part, alpha, tsum);
+            } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int col = col0 + i;
@@ -503,14 +541,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float gv = 0.f;
               if (row_ok && col < p.N) {
                 if (!(p.dcl && is_diag)) {
-                  if (p.w_row != 0.f) gv += w_row * exp2f(acc_v * a2 - lr2);
+                  if (p.w_row != 0.f) gv += w_row * nce_ex2(acc_v * a2 - lr2);
                   if (p.w_col != 0.f)
-                    gv += w_col * exp2f(acc_v * a2 - __ldg(p.lse_col + col) * 1.4426950408889634f);
+                    gv += w_col * nce_ex2(acc_v * a2 - __ldg(p.lse_col + col) * 1.4426950408889634f);
                 }
                 if (is_diag) gv -= w_diag;
                 tsum += gv * acc_v * alpha;
               }
               gq[i] = gv * alpha;   // temperature folded in: d rows = gq @ cols; 0 beyond N / M
+            }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {

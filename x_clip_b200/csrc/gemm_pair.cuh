@@ -277,7 +277,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int hcol = n_blk * 128 + bs * 64;               // hidden-unit column of this box
         const int r0 = m_blk * kGemmBlockM;
 #pragma unroll
-        for (int which = 0; which < 3; ++which) {
+        for (int which = p.ff_skip_u ? 2 : 0; which < 3; ++which) {
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
           const uint32_t* src = which == 0 ? pv : (which == 1 ? pg : ph);

@@ -146,6 +146,9 @@ class TransformerFn(torch.autograd.Function):
         mask_c = None if mask is None else mask.contiguous()
 
         saved, ff_saved = [], []
+        # under torch.no_grad() (the first sweep of the micro-batched step, inference) nothing is
+        # kept for a backward: the 8d-wide u = [value | gate] is then not even written
+        need_bwd = any(ctx.needs_input_grad)
         # bf16 MMA operands of this call's weights; backward reuses exactly these (ctx.wb)
         wb = [tuple(weight_bf16(w) for w in (l[1], l[2], l[5], l[7])) for l in layers]
         # norm_in fused with the first pre-norm
@@ -163,7 +166,7 @@ class TransformerFn(torch.autograd.Function):
                 # h below is hp = value*gelu(gate) BEFORE the LayerNorm (the norm is folded into
                 # the down-projection); the backward knows from ctx.fused_ff
                 w1p, w2g, colvec = ff_weights(w1, w2, g4)
-                u, h, rowsum = K.ff_up(xn2, w1p)
+                u, h, rowsum = K.ff_up(xn2, w1p, need_u=need_bwd)
                 x2, acc, st_v = K.ff_down(h, w2g, colvec, rowsum, x1, LN_EPS)
                 ff_saved.append((w2g, colvec, acc))
             else:
