@@ -129,7 +129,7 @@ class Transformer(nn.Module):
             ang = rotary_pos_emb[:, :16].to(device=x.device, dtype=torch.float32)
             cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
         return E.TransformerFn.apply(x, mask, self.heads, self.depth, self.causal, cos, sin,
-                                     *self.flat_weights())
+                                     torch.is_grad_enabled(), *self.flat_weights())
 
 
 class PatchDropout(nn.Module):

@@ -176,16 +176,6 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
         tma_load_3d(sK, &tm_qkv, qk_bar, inner + h * kSDh, 0, b);
         mbar_arrive_expect_tx(v_bar, kBox);
         tma_load_3d(sV, &tm_qkv, v_bar, 2 * inner + h * kSDh, 0, b);
-        {   // the CTA's NEXT item travels HBM -> L2 while this one is computed (the kernel is
-            // HBM-latency bound: shared memory of 4 CTAs / SM leaves no room for a second stage)
-          const int bh2 = bh + (int)gridDim.x;
-          if (bh2 < total) {
-            const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
-            tma_prefetch_l2_3d(&tm_qkv, h2 * kSDh, 0, b2);
-            tma_prefetch_l2_3d(&tm_qkv, inner + h2 * kSDh, 0, b2);
-            tma_prefetch_l2_3d(&tm_qkv, 2 * inner + h2 * kSDh, 0, b2);
-          }
-        }
         if (it > 0) mbar_wait(e_bar, par ^ 1);   // O of the previous item was read out of TMEM
         mbar_wait(qk_bar, par);
         tcgen05_fence_after();
@@ -479,16 +469,6 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         mbar_arrive_expect_tx(vdo_bar, 2 * box);
         tma_load_3d(sP, &tm_qkv, vdo_bar, 2 * inner + h * kSDh, 0, b);
         tma_load_3d(sdO, &tm_do, vdo_bar, h * kSDh, 0, b);
-        {   // next item HBM -> L2 (see the forward kernel)
-          const int bh2 = bh + (int)gridDim.x;
-          if (bh2 < total) {
-            const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
-            tma_prefetch_l2_3d(&tm_qkv, h2 * kSDh, 0, b2);
-            tma_prefetch_l2_3d(&tm_qkv, inner + h2 * kSDh, 0, b2);
-            tma_prefetch_l2_3d(&tm_qkv, 2 * inner + h2 * kSDh, 0, b2);
-            tma_prefetch_l2_3d(&tm_do, h2 * kSDh, 0, b2);
-          }
-        }
         if (it > 0) mbar_wait(e_bar, par ^ 1);   // dQ/dK/dV of the previous item left TMEM
         mbar_wait(qk_bar, par);
         tcgen05_fence_after();

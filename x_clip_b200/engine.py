@@ -133,7 +133,8 @@ class TransformerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, mask, heads: int, depth: int, causal: bool, rot_cos, rot_sin, *weights):
+    def forward(ctx, x, mask, heads: int, depth: int, causal: bool, rot_cos, rot_sin, need_bwd: bool,
+                *weights):
         B, n, d = x.shape
         M = B * n
         scale = 64 ** -0.5
@@ -146,9 +147,9 @@ class TransformerFn(torch.autograd.Function):
         mask_c = None if mask is None else mask.contiguous()
 
         saved, ff_saved = [], []
-        # under torch.no_grad() (the first sweep of the micro-batched step, inference) nothing is
-        # kept for a backward: the 8d-wide u = [value | gate] is then not even written
-        need_bwd = any(ctx.needs_input_grad)
+        # need_bwd = torch.is_grad_enabled() at the call site (inside forward() it is always off and
+        # needs_input_grad ignores no_grad): in the first sweep of the micro-batched step and in
+        # inference nothing is kept for a backward, and the 8d-wide u = [value | gate] is not written
         # bf16 MMA operands of this call's weights; backward reuses exactly these (ctx.wb)
         wb = [tuple(weight_bf16(w) for w in (l[1], l[2], l[5], l[7])) for l in layers]
         # norm_in fused with the first pre-norm
@@ -258,7 +259,7 @@ class TransformerFn(torch.autograd.Function):
         grads[0] = dg_in
         wg.join()
         ctx.saved = ctx.wb = None
-        return (dx_in.view(B, n, d), None, None, None, None, None, None, *grads)
+        return (dx_in.view(B, n, d), None, None, None, None, None, None, None, *grads)
 
 
 class TextEmbedFn(torch.autograd.Function):
