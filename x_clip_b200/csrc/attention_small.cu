@@ -34,7 +34,6 @@ struct AttnSmallFwdParams {
   bf16* o;
   long long ldo;
   float* lse;              // [B, H, n] base-2 log-sum-exp of the scaled, masked scores
-  int sms;                 // SM count: CTAs b, b + sms, b + 2 sms ... usually share an SM
 };
 
 __device__ __forceinline__ float sm_ex2(float x) {
@@ -167,15 +166,6 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
       const uint32_t idesc_s = make_idesc_bf16(128, p.nkp, kMajorK, kMajorK);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, kSDh, kMajorK, kMajorMN);
       const int ksteps = p.nkp / 16;
-      // The co-resident CTAs of an SM start together and do identical work per item, so they would
-      // stay in lock-step: all loading, then all computing - HBM and the SM never overlap (ncu: load
-      // time + issue time = item time).  A one-off start offset of ~1/4 item per residency wave
-      // de-phases them.
-      {
-        const long long wave = blockIdx.x / p.sms;
-        const long long t0 = clock64();
-        while (clock64() - t0 < wave * 3500) { }
-      }
       uint32_t it = 0;
       for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++it) {
         const int b = bh / p.H, h = bh - b * p.H;
@@ -380,7 +370,6 @@ struct AttnSmallBwdParams {
   const float* delta;    // [B, H, n] rowsum(dO * O)
   bf16* dqkv;            // [B*n, ld]: dq | dk | dv
   long long ld;
-  int sms;
 };
 
 constexpr int kSBwdComputeWarps = 8;
@@ -469,11 +458,6 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv,
       const uint64_t desc_domn = make_smem_desc(smem_u32(sdO), 8192, 1024);
       const int ksteps = p.nkp / 16;
       const uint32_t blk16 = static_cast<uint32_t>(box) >> 4;
-      {   // de-phase the two CTAs of an SM (see the forward kernel)
-        const long long wave = blockIdx.x / p.sms;
-        const long long t0 = clock64();
-        while (clock64() - t0 < wave * 9000) { }
-      }
       uint32_t it = 0;
       for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++it) {
         const int b = bh / p.H, h = bh - b * p.H;
@@ -679,7 +663,7 @@ int attn_bwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, con
   p.B = B; p.H = heads; p.n = n; p.nkp = (n + 15) / 16 * 16;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.mask = key_mask; p.lse = lse; p.delta = delta;
-  p.dqkv = reinterpret_cast<bf16*>(dqkv); p.ld = ld_dqkv; p.sms = num_sms();
+  p.dqkv = reinterpret_cast<bf16*>(dqkv); p.ld = ld_dqkv;
   CUtensorMap tq, tdo;
   int rc = encode_3d_bf16(&tq, qkv, (uint64_t)(3 * heads * kSDh), (uint64_t)n, (uint64_t)B,
                           (uint64_t)ld_qkv, (uint64_t)n * ld_qkv, kSDh, (uint32_t)p.nkp);
@@ -718,7 +702,6 @@ int attn_fwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, voi
   p.o = reinterpret_cast<bf16*>(o);
   p.ldo = ldo;
   p.lse = lse;
-  p.sms = num_sms();
   if (n <= 64)
     return causal ? launch_fwd_small<64, true>(qkv, ld_qkv, p, stream)
                   : launch_fwd_small<64, false>(qkv, ld_qkv, p, stream);
