@@ -328,14 +328,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
           const int kq = n_blk * BLOCK_N + bhalf * 128 + q * 64;
-          // coalesced fetch of THIS warp's part of the slab (32 rows x its 4 chunks = 64 bytes per row):
-          // iteration t covers rows 8t..8t+7, lane = (row%8)*4 + chunk.  The region (its quarter's rows x
-          // its 4 chunks) of both boxes is private to the warp, so the transposition needs no block barrier.
+          // coalesced fetch: iteration t covers slab rows 4t..4t+3 (this warp: t = 4 part .. 4 part + 3),
+          // lane = (row%4)*8 + 16-byte chunk
           uint4 rawv[4], rawg[4];
 #pragma unroll
           for (int t4 = 0; t4 < 4; ++t4) {
-            const int rr = slab_row0 + t4 * 8 + (lane >> 2);
-            const bf16* src = p.ff_u + (long long)(rr < p.M ? rr : 0) * p.ff_ldu + kq + (part * 4 + (lane & 3)) * 8;
+            const int rr = slab_row0 + (part * 4 + t4) * 4 + (lane >> 3);
+            const bf16* src = p.ff_u + (long long)(rr < p.M ? rr : 0) * p.ff_ldu + kq + (lane & 7) * 8;
             rawv[t4] = *reinterpret_cast<const uint4*>(src);
             rawg[t4] = *reinterpret_cast<const uint4*>(src + p.ff_hidden);
           }
@@ -343,14 +342,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           asm volatile("bar.sync %0, 256;" ::"r"(1 + bhalf) : "memory");   // previous stores have read the boxes
 #pragma unroll
           for (int t4 = 0; t4 < 4; ++t4) {
-            const int r = quarter * 32 + t4 * 8 + (lane >> 2);
-            const uint32_t off = swz128(r, part * 4 + (lane & 3));
+            const int r = quarter * 32 + (part * 4 + t4) * 4 + (lane >> 3);
+            const uint32_t off = swz128(r, lane & 7);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(rawv[t4].x),
                          "r"(rawv[t4].y), "r"(rawv[t4].z), "r"(rawv[t4].w) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(rawg[t4].x),
                          "r"(rawg[t4].y), "r"(rawg[t4].z), "r"(rawg[t4].w) : "memory");
           }
-          __syncwarp();
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + bhalf) : "memory");   // both warps of a quarter filled it
 #pragma unroll
           for (int c16 = 0; c16 < 2; ++c16) {
             uint32_t v[16];
