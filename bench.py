@@ -607,7 +607,8 @@ def main():
             ratio = json.loads(tf.read_text()).get("traffic_over_algorithmic")
             if ratio:
                 traffic = round(ratio * sum(d["bytes"] for d in gem) / g_calls)
-        roofline = {"kernel": "gemm_bf16_kernel (tcgen05, fwd+dgrad+wgrad launches)",
+        roofline = {"kernel": "gemm_pair_kernel / gemm_bf16_kernel (tcgen05, plain-epilogue fwd+dgrad+wgrad launches; "
+                              "the fused feed-forward GEMMs are listed under feed_forward_fused)",
                     "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4),
                     "frac_of_burst_peak": round(achieved / peak_burst, 4), "traffic": traffic,
@@ -631,6 +632,14 @@ def main():
                     "tensor_frac_of_burst_peak": round(ft, 4), "hbm_gbs": round(gbs, 1),
                     "hbm_frac_of_peak": round(fh, 4), "bound": "hbm" if fh > ft else "tensor",
                     "frac": round(max(ft, fh), 4), "note": note_txt}
+        roofline["feed_forward_fused"] = {
+            "up": sub(["ff_up"], "gemm_pair_kernel<PEPI_FF_UP> (up-projection GEMM + GEGLU epilogue)",
+                      "flops = the GEMM only (2*M*8d*d); the epilogue also evaluates 4d GELUs per token and writes "
+                      "u (8d, skipped in forward-only sweeps) + hp (4d)"),
+            "down": sub(["ff_down"], "gemm_pair_kernel<PEPI_FF_DOWN> (down-projection GEMM + LayerNorm fold + residual)",
+                        "flops = the GEMM only (2*M*4d*d)"),
+            "bwd": sub(["ff_bwd"], "gemm_pair_kernel<PEPI_FF_BWD> (dgrad GEMM + LayerNorm/GEGLU backward epilogue)",
+                       "flops = the GEMM only (2*M*4d*d); reads u 8d, writes du 8d: HBM-bound by design")}
         roofline["attention"] = {
             "fwd": sub(["attn_fwd"], "attn_fwd_small_kernel / attn_fwd_wg_kernel",
                        "algorithmic: 4 n^2 64 flops and q,k,v read + o write per (batch, head); at n = 98 / 78 "

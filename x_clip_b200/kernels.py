@@ -311,7 +311,7 @@ def ff_up(x, w1p, need_u=True):
     u = torch.empty((M, 8 * d), device=x.device, dtype=BF16) if need_u else None
     hp = torch.empty((M, 4 * d), device=x.device, dtype=BF16)
     rowsum = torch.zeros((M, 2), device=x.device, dtype=F32)
-    _call(x, "gemm_fwd", 2.0 * M * 8 * d * d, 2.0 * (M * d + 8 * d * d + M * (12 if need_u else 4) * d), "xclip_ff_up",
+    _call(x, "ff_up", 2.0 * M * 8 * d * d, 2.0 * (M * d + 8 * d * d + M * (12 if need_u else 4) * d), "xclip_ff_up",
           x.data_ptr(), x.stride(0), w1p.data_ptr(), _ptr(u), u.stride(0) if need_u else 0, hp.data_ptr(),
           hp.stride(0), rowsum.data_ptr(), M, d)
     return u, hp, rowsum
@@ -325,7 +325,7 @@ def ff_down(hp, w2g, colvec, rowsum, res, eps):
     out = torch.empty((M, d), device=hp.device, dtype=BF16)
     acc = torch.empty((M, d), device=hp.device, dtype=BF16)
     stats = torch.empty((M, 2), device=hp.device, dtype=F32)
-    _call(hp, "gemm_fwd", 2.0 * M * d * 4 * d, 2.0 * (M * 4 * d + 4 * d * d + 3 * M * d), "xclip_ff_down",
+    _call(hp, "ff_down", 2.0 * M * d * 4 * d, 2.0 * (M * 4 * d + 4 * d * d + 3 * M * d), "xclip_ff_down",
           hp.data_ptr(), hp.stride(0), w2g.data_ptr(), colvec.data_ptr(), rowsum.data_ptr(),
           res.data_ptr(), res.stride(0), out.data_ptr(), out.stride(0), acc.data_ptr(), acc.stride(0),
           stats.data_ptr(), float(eps), M, d)
@@ -355,7 +355,7 @@ def ff_bwd(dx, w2g, u, stats, ab):
     _need(stats, F32, "stats"); _need(ab, F32, "ab")
     M, d = dx.shape
     du = torch.empty((M, 8 * d), device=dx.device, dtype=BF16)
-    _call(dx, "gemm_dgrad", 2.0 * M * 4 * d * d, 2.0 * (M * d + 4 * d * d + 16 * M * d), "xclip_ff_bwd",
+    _call(dx, "ff_bwd", 2.0 * M * 4 * d * d, 2.0 * (M * d + 4 * d * d + 16 * M * d), "xclip_ff_bwd",
           dx.data_ptr(), dx.stride(0), w2g.data_ptr(), u.data_ptr(), u.stride(0), stats.data_ptr(),
           ab.data_ptr(), du.data_ptr(), du.stride(0), M, d)
     return du
