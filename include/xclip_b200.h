@@ -110,9 +110,6 @@ int xclip_cast_f32_bf16(const float* src, void* dst, int64_t n, xclip_stream_t s
  * qkv bf16 [B*n, ld_qkv] holds q | k | v, each heads*64 wide, head-major inside.
  * key_mask uint8 [B, n] (1 = attend; may be NULL).  o bf16 [B*n, ldo] (heads merged).
  * lse f32 [B, heads, n]: base-2 log-sum-exp of scale*log2(e)*scores (saved for backward). */
-/* 64 < n <= 128 forward: 1 (default) = two-threads-per-row pipelined kernel, 0 = the one-thread-per-row
- * kernel also used for n <= 64.  Same results; a measurement switch.  Returns the previous value. */
-int xclip_attn_set_mid_kernel(int enabled);
 int xclip_attn_fwd(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o, int64_t ldo,
                    float* lse, int B, int n, int heads, float scale, int causal,
                    xclip_stream_t stream);

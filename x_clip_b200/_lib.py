@@ -51,7 +51,6 @@ SIGNATURES = {
                                  c_int, c_void_p]),
     "xclip_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "xclip_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
-    "xclip_attn_set_mid_kernel": (c_int, [c_int]),
     "xclip_attn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                c_int, c_int, c_float, c_int, c_void_p]),
     "xclip_attn_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,

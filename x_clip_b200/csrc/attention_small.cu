@@ -110,33 +110,6 @@ __device__ __forceinline__ void sm_scores(const uint32_t (&v)[32], float (&t)[32
   }
 }
 
-// in-place variant (v holds the raw fp32 accumulator bits on entry, the scaled/masked scores on exit);
-// entries >= CNT are set to -inf
-template <int CNT, bool kCausal>
-__device__ __forceinline__ void sm_scores_inplace(uint32_t (&v)[32], bool fast, int valid, float c,
-                                                  uint32_t mul_addr, uint32_t add_addr, int col0, int row) {
-  if (fast) {
-#pragma unroll
-    for (int i = 0; i < CNT; ++i)
-      v[i] = __float_as_uint((valid >= CNT || i < valid) ? __uint_as_float(v[i]) * c : -INFINITY);
-  } else {
-#pragma unroll
-    for (int i = 0; i < CNT; i += 4) {
-      const float4 m = sm_lds_f4(mul_addr + i * 4);
-      const float4 a = sm_lds_f4(add_addr + i * 4);
-      const float mm[4] = {m.x, m.y, m.z, m.w}, aa[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float t = fmaf(__uint_as_float(v[i + u]), mm[u], aa[u]);
-        if (kCausal && col0 + i + u > row) t = fminf(t, -FLT_MAX);
-        v[i + u] = __float_as_uint(i + u < valid ? t : -INFINITY);   // (select: stale bits may be NaN)
-      }
-    }
-  }
-#pragma unroll
-  for (int i = CNT; i < 32; ++i) v[i] = 0xff800000u;
-}
-
 template <int ROWS, bool kCausal>
 __global__ void __launch_bounds__((ROWS / 32 + 1) * 32, ROWS == 128 ? 4 : 8)
 attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmallFwdParams p) {
@@ -364,283 +337,6 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
     tcgen05_fence_after();
     tmem_dealloc<ROWS>(tmem_base);
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Forward for 64 < n <= 128, second generation ("mid" kernel): a 2-stage operand pipeline INSIDE the
-// CTA and two threads per query row.
-//
-// The one-thread-per-row kernel above reaches ~0.45 of the HBM roofline at n = 98: every CTA runs
-// load -> S -> softmax -> PV -> store strictly in sequence, the softmax alone is ~1700 instructions
-// per thread (two passes over TMEM), and with four CTAs per SM nothing is left for a second stage.
-// Here: 8 softmax warps (a row is shared by two threads, key columns [0,64) and [64, nkp)), each half
-// keeps its scores in registers (one TMEM read), its own (max, sum) and its own 64-column O
-// accumulator (O_h = P_h V_h) - no cross-thread exchange until the epilogue, which combines
-// O = (2^(m0-m) O_0 + 2^(m1-m) O_1) / (2^(m0-m) l0 + 2^(m1-m) l1).  Q/K/V boxes (ceil16(n) rows) of
-// the NEXT item are fetched into the other smem stage while the current item is processed; S of the
-// next item is issued as soon as the softmax has consumed the current S; the epilogue of item i-1
-// runs after the softmax of item i.  TMEM: S 128 + O_0 64 + O_1 64 = 256 columns -> 2 CTAs per SM.
-constexpr int kMidWarps = 8;
-constexpr int kMidThreads = (kMidWarps + 1) * 32;
-
-__host__ __device__ constexpr int fwd_mid_smem_bytes(int nkp) { return 2 * 3 * nkp * 128 + 256 + 2 * 2 * 128 * 4 + 4 * 2 * 128 * 8; }
-
-template <bool kCausal>
-__global__ void __maxnreg__(112)
-attn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmallFwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int box = p.nkp * 128;                   // bytes of one [nkp x 64] bf16 TMA box
-  const int stage_bytes = 3 * box;               // Q | K | V ; P overwrites Q | K
-  uint8_t* tail = smem + 2 * stage_bytes;
-  uint64_t* qk_bar = reinterpret_cast<uint64_t*>(tail);   // [2]
-  uint64_t* v_bar = qk_bar + 2;                            // [2]
-  uint64_t* s_bar = qk_bar + 4;
-  uint64_t* p_bar = qk_bar + 5;
-  uint64_t* o_bar = qk_bar + 6;
-  uint64_t* e_bar = qk_bar + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qk_bar + 8);
-  const uint32_t sFlag = smem_u32(tail + 128);             // [2][4] u32
-  const uint32_t sMul = smem_u32(tail + 256);              // [2][128] f32
-  const uint32_t sAdd = sMul + 2 * 128 * 4;                // [2][128] f32
-  const uint32_t sStat = sAdd + 2 * 128 * 4;               // [4 items][2 halves][128 rows] float2 (max, sum)
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const bool is_control = warp == kMidWarps;
-
-  if (threadIdx.x == 0) {
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    for (int i = 0; i < 2; ++i) { mbar_init(&qk_bar[i], 1); mbar_init(&v_bar[i], 1); }
-    mbar_init(s_bar, 1);
-    mbar_init(p_bar, kMidWarps);
-    mbar_init(o_bar, 1);
-    mbar_init(e_bar, kMidWarps);
-    fence_barrier_init();
-  }
-  if (is_control) {
-    if (lane == 0) tma_prefetch_desc(&tm_qkv);
-    sm_tmem_alloc<256>(tmem_slot);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO0 = tmem_base + 128, tO1 = tmem_base + 192;
-  const int inner = p.H * kSDh;
-  const int total = p.B * p.H;
-  const int nitems = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
-
-  if (is_control) {
-    if (XCLIP_ONE_LANE(lane)) {
-      const uint32_t idesc_s = make_idesc_bf16(128, p.nkp, kMajorK, kMajorK);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, kSDh, kMajorK, kMajorMN);
-      const int k1 = (p.nkp - 64) / 16;                    // k-steps of the second key half (1..4)
-      auto load = [&](int i) {
-        const int bh = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = bh / p.H, h = bh - b * p.H;
-        uint8_t* st = smem + (i & 1) * stage_bytes;
-        mbar_arrive_expect_tx(&qk_bar[i & 1], 2 * box);
-        tma_load_3d(st, &tm_qkv, &qk_bar[i & 1], h * kSDh, 0, b);
-        tma_load_3d(st + box, &tm_qkv, &qk_bar[i & 1], inner + h * kSDh, 0, b);
-        mbar_arrive_expect_tx(&v_bar[i & 1], box);
-        tma_load_3d(st + 2 * box, &tm_qkv, &v_bar[i & 1], 2 * inner + h * kSDh, 0, b);
-      };
-      auto issue_s = [&](int i) {
-        const uint32_t st = smem_u32(smem + (i & 1) * stage_bytes);
-        const uint64_t dq = make_smem_desc(st, 0, 1024), dk = make_smem_desc(st + box, 0, 1024);
-#pragma unroll
-        for (int k = 0; k < kSDh / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_bar);
-      };
-      if (nitems > 0) {
-        load(0);
-        if (nitems > 1) load(1);
-        mbar_wait(&qk_bar[0], 0);
-        tcgen05_fence_after();
-        issue_s(0);
-      }
-      for (int i = 0; i < nitems; ++i) {
-        mbar_wait(p_bar, i & 1);                 // P(i) in smem, S(i) consumed
-        if (i + 1 < nitems) {
-          mbar_wait(&qk_bar[(i + 1) & 1], ((i + 1) >> 1) & 1);
-          tcgen05_fence_after();
-          issue_s(i + 1);
-        }
-        if (i >= 1) mbar_wait(e_bar, (i - 1) & 1);   // O_0 / O_1 of the previous item were read out
-        mbar_wait(&v_bar[i & 1], (i >> 1) & 1);
-        tcgen05_fence_after();
-        {
-          const uint32_t st = smem_u32(smem + (i & 1) * stage_bytes);
-          const uint64_t dp0 = make_smem_desc(st, 0, 1024), dp1 = make_smem_desc(st + box, 0, 1024);
-          const uint64_t dv = make_smem_desc(st + 2 * box, 8192, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)            // keys [0, 64)
-            umma_bf16(tO0, dp0 + 2 * k, dv + k * 128, idesc_pv, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {          // keys [64, nkp)
-            if (k < k1) umma_bf16(tO1, dp1 + 2 * k, dv + (4 + k) * 128, idesc_pv, k > 0 ? 1u : 0u);
-          }
-          umma_commit(o_bar);
-        }
-        if (i + 2 < nitems) {                    // the stage is free once PV(i) retired
-          mbar_wait(o_bar, i & 1);
-          load(i + 2);
-        }
-      }
-      if (nitems > 0) mbar_wait(o_bar, (nitems - 1) & 1);
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp & 3, half = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const bool alive = quarter * 32 < p.n;
-    const int c_lo = half * 64;                           // this thread's key columns [c_lo, c_hi)
-    const int c_hi = half == 0 ? 64 : p.nkp;
-    const int ncols = c_hi - c_lo;                        // 64 (half 0) or 16..64 (half 1)
-    const float c = p.scale_log2;
-    float own_m = 0.f, own_l = 0.f;                       // statistics of the previous item (for its epilogue)
-
-    auto epilogue = [&](int k, float m_own, float l_own) {
-      const int bh = (int)blockIdx.x + k * (int)gridDim.x;
-      const int b = bh / p.H, h = bh - b * p.H;
-      mbar_wait(o_bar, k & 1);
-      tcgen05_fence_after();
-      if (alive) {
-        const float2 other = *reinterpret_cast<const float2*>(
-            __cvta_shared_to_generic(sStat + ((((k & 3) * 2 + (half ^ 1)) * 128 + row) * 8)));
-        const float m0 = half == 0 ? m_own : other.x, m1 = half == 0 ? other.x : m_own;
-        const float l0 = half == 0 ? l_own : other.y, l1 = half == 0 ? other.y : l_own;
-        const float m = fmaxf(m0, m1);
-        const float a0 = sm_ex2(m0 - m), a1 = sm_ex2(m1 - m);
-        const float L = a0 * l0 + a1 * l1;
-        const float inv = 1.f / L;
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(tO0 + lane_off + half * 32, v0);
-        tmem_ld_32x32(tO1 + lane_off + half * 32, v1);
-        tmem_ld_wait();
-        if (row < p.n) {
-          if (half == 0) p.lse[((long long)b * p.H + h) * p.n + row] = m + log2f(L);
-          bf16* dst = p.o + ((long long)b * p.n + row) * p.ldo + h * kSDh + half * 32;
-          const float w0 = a0 * inv, w1 = a1 * inv;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              f[e] = __uint_as_float(v0[i + e]) * w0 + __uint_as_float(v1[i + e]) * w1;
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(dst + i) = o;
-          }
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(e_bar);
-    };
-
-    for (int i = 0; i < nitems; ++i) {
-      const int bh = (int)blockIdx.x + i * (int)gridDim.x;
-      const int b = bh / p.H;
-      const uint32_t par = i & 1;
-      // ---- per-key tables (double buffered by item parity) + "any key masked" flag
-      if (threadIdx.x < 128) {
-        const int j = threadIdx.x;
-        float mul = 0.f, add = -INFINITY;
-        bool masked = false;
-        if (j < p.n) {
-          const bool keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
-          mul = keep ? c : 0.f;
-          add = keep ? 0.f : -FLT_MAX;
-          masked = !keep;
-        }
-        sm_sts_f(sMul + (par * 128 + j) * 4, mul);
-        sm_sts_f(sAdd + (par * 128 + j) * 4, add);
-        const uint32_t any = __ballot_sync(0xffffffffu, masked);
-        if (lane == 0) sm_sts_u32(sFlag + (par * 4 + warp) * 4, any);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      uint32_t anym = 0;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) anym |= sm_lds_u32(sFlag + (par * 4 + w) * 4);
-      const bool fast = !kCausal && anym == 0;
-      const uint32_t mulb = sMul + par * 128 * 4, addb = sAdd + par * 128 * 4;
-      const uint32_t pblk = smem_u32(smem + (i & 1) * stage_bytes) + half * box;   // this half's P block
-
-      mbar_wait(s_bar, par);
-      tcgen05_fence_after();
-      float m2 = -INFINITY, sum = 0.f;
-      if (alive) {
-        // scores of this thread's columns stay in registers: one TMEM read per item
-        // always 64 columns: columns beyond nkp hold stale TMEM bits, the select in
-        // sm_scores_inplace turns every column >= n into -inf without touching its value
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(tS + lane_off + c_lo, va);
-        tmem_ld_32x32(tS + lane_off + c_lo + 32, vb);
-        tmem_ld_wait();
-        sm_scores_inplace<32, kCausal>(va, fast, p.n - c_lo, c, mulb + c_lo * 4, addb + c_lo * 4, c_lo, row);
-        sm_scores_inplace<32, kCausal>(vb, fast, p.n - c_lo - 32, c, mulb + (c_lo + 32) * 4, addb + (c_lo + 32) * 4,
-                                       c_lo + 32, row);
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          m2 = fmaxf(m2, fmaxf(fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])),
-                               fmaxf(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3]))));
-          m2 = fmaxf(m2, fmaxf(fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])),
-                               fmaxf(__uint_as_float(vb[e + 2]), __uint_as_float(vb[e + 3]))));
-        }
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          const int col = cc * 8;                          // column inside this half
-          if (col < ncols) {
-            float e8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              e8[e] = sm_ex2(__uint_as_float(cc < 4 ? va[cc * 8 + e] : vb[(cc - 4) * 8 + e]) - m2);
-            sum += ((e8[0] + e8[1]) + (e8[2] + e8[3])) + ((e8[4] + e8[5]) + (e8[6] + e8[7]));
-            sm_sts_v4(pblk + swz128(row, cc), pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]),
-                      pack_bf16x2(e8[4], e8[5]), pack_bf16x2(e8[6], e8[7]));
-          }
-        }
-        *reinterpret_cast<float2*>(__cvta_shared_to_generic(sStat + ((((i & 3) * 2 + half) * 128 + row) * 8))) =
-            make_float2(m2, sum);
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_bar);
-
-      if (i >= 1) epilogue(i - 1, own_m, own_l);           // deferred behind this item's softmax
-      own_m = m2;
-      own_l = sum;
-    }
-    if (nitems > 0) epilogue(nitems - 1, own_m, own_l);
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (is_control) {
-    tcgen05_fence_after();
-    tmem_dealloc<256>(tmem_base);
-  }
-}
-
-template <bool kCausal>
-static int launch_fwd_mid(const void* qkv, int64_t ld_qkv, const AttnSmallFwdParams& p, cudaStream_t stream) {
-  CUtensorMap tm;
-  int rc = encode_3d_bf16(&tm, qkv, (uint64_t)(3 * p.H * kSDh), (uint64_t)p.n, (uint64_t)p.B,
-                          (uint64_t)ld_qkv, (uint64_t)p.n * ld_qkv, kSDh, (uint32_t)p.nkp);
-  if (rc) return rc;
-  auto kern = attn_fwd_mid_kernel<kCausal>;
-  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), fwd_mid_smem_bytes(128));
-  if (rc) return rc;
-  const int smem = fwd_mid_smem_bytes(p.nkp);
-  long long grid = (long long)num_sms() * 2;
-  if (grid > (long long)p.B * p.H) grid = (long long)p.B * p.H;
-  kern<<<(int)grid, kMidThreads, smem, stream>>>(tm, p);
-  XCLIP_LAUNCH_CHECK("attn_fwd_mid_kernel");
-  return XCLIP_OK;
 }
 
 template <int ROWS, bool kCausal>
@@ -993,8 +689,6 @@ int attn_bwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, con
   return XCLIP_OK;
 }
 
-static int g_fwd_mid = 1;
-
 // host entry used by xclip_attn_fwd (attention_fwd.cu) for n <= 128
 int attn_fwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, void* o, int64_t ldo,
                    float* lse, int B, int n, int heads, float scale, int causal,
@@ -1011,18 +705,8 @@ int attn_fwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, voi
   if (n <= 64)
     return causal ? launch_fwd_small<64, true>(qkv, ld_qkv, p, stream)
                   : launch_fwd_small<64, false>(qkv, ld_qkv, p, stream);
-  if (g_fwd_mid)     // 64 < n <= 128: two threads per row, register-resident scores, 2-stage pipeline
-    return causal ? launch_fwd_mid<true>(qkv, ld_qkv, p, stream) : launch_fwd_mid<false>(qkv, ld_qkv, p, stream);
   return causal ? launch_fwd_small<128, true>(qkv, ld_qkv, p, stream)
                 : launch_fwd_small<128, false>(qkv, ld_qkv, p, stream);
 }
 
 }  // namespace xclip
-
-// A/B switch for measurements (process-wide, explicit - no environment variables): 0 selects the
-// one-thread-per-row kernel for 64 < n <= 128 as well.  Returns the previous setting.
-extern "C" int xclip_attn_set_mid_kernel(int enabled) {
-  const int prev = xclip::g_fwd_mid;
-  xclip::g_fwd_mid = enabled ? 1 : 0;
-  return prev;
-}
