@@ -193,10 +193,12 @@ int xclip_text_embed_bwd(const int64_t* ids, const void* dx, float* dtok, float*
  *                     holds 128 value rows and the 128 MATCHING gate rows.
  *   ff_scale_cast   : w2g = bf16(net.4.weight [d, 4d] * net.2.g [4d]) and colvec[j] = sum_k w2g[j,k].
  *   ff_up           : u = [value | gate] bf16 [M, 8d] (reference layout, kept for the backward),
- *                     hp = value * gelu_erf(gate) bf16 [M, 4d], rowsum[r] += (sum hp, sum hp^2)
- *                     (rowsum f32 [M, 2], zeroed by the caller) - one GEMM, GEGLU in its epilogue.
+ *                     hp = value * gelu_erf(gate) bf16 [M, 4d], rowsum[r, box] = (sum hp, sum hp^2) of
+ *                     every 64-column box (rowsum f32 [M, 4d/64, 2], fully overwritten: no atomics,
+ *                     bit-reproducible) - one GEMM, GEGLU in its epilogue.
  *                     u may be NULL (forward-only sweeps: two thirds of the output traffic saved).
- *   ff_down         : out = rstd_r * (hp w2g^T - mean_r * colvec) + residual  (== LN(hp) g W2^T + x1),
+ *   ff_down         : (mean_r, rstd_r) from rowsum; out = rstd_r * (hp w2g^T - mean_r * colvec) + residual
+ *                     (== LN(hp) g W2^T + x1),
  *                     acc_out = bf16(hp w2g^T), stats[r] = (mean, rstd) - one GEMM.
  *   ff_bwd_prep     : dxs = bf16(dx * rstd_r) [M, d]; vsum[j] += sum_r dxs[r,j] * mean_r; with acc and
  *                     colvec also ab[r] = (mean_k gdh, mean_k gdh*hn) - the two row means of the

@@ -225,9 +225,7 @@ def test_microbatched_step_equals_single_pass(cuda_device):
         loss.backward()
         res.append((loss.item(), {k: p.grad.clone() for k, p in clip.named_parameters() if p.grad is not None}))
     for loss, grads in res[1:]:
-        # (the fused feed-forward accumulates LayerNorm row sums with fp32 atomics: the summation
-        # order, hence the last bits of the statistics, vary from launch to launch)
-        assert abs(loss - res[0][0]) < 1e-4
+        assert abs(loss - res[0][0]) < 1e-5
         assert grads.keys() == res[0][1].keys()
         for k, g in grads.items():
             ref = res[0][1][k]
@@ -245,7 +243,7 @@ def test_microbatched_step_equals_single_pass(cuda_device):
         loss = clip(text, image, return_loss=True)
         loss.backward()
         out.append((loss.item(), clip.to_visual_latent.weight.grad.clone()))
-    assert abs(out[0][0] - out[1][0]) < 1e-4 and torch.isfinite(out[0][1]).all()
+    assert out[0][0] == out[1][0] and torch.isfinite(out[0][1]).all()      # the forward is bit-reproducible
     assert (out[0][1] - out[1][1]).abs().max().item() <= 1e-3 * out[0][1].abs().max().item()
 
 

@@ -59,7 +59,7 @@ struct GemmParams {
   float* seg_max;          // [M, n_segs]  max_i s
   int* seg_arg;            // [M, n_segs]  argmax (index inside the segment)
   // ---- fused feed-forward epilogues of the CTA-pair kernel (gemm_pair.cuh)
-  float* ff_rowsum;        // [M,2] (sum, sum of squares) of the GEGLU output rows: UP accumulates, DOWN reads
+  float* ff_rowsum;        // [M, 4d/64, 2] per-box (sum, sum of squares) of the GEGLU output rows: UP writes, DOWN sums
   const float* ff_colvec;  // DOWN: c[N] = row sums of the gain-scaled down-projection weight
   float* ff_stats;         // DOWN: [M,2] (mean, rstd) of the GEGLU output rows, written for the backward
   float ff_eps;            // LayerNorm epsilon

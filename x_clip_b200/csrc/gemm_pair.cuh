@@ -301,9 +301,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s1 += o.x;
           s2 += o.y;
         }
+        // one (sum, sum^2) slot per row and 64-column box: plain stores, summed in a fixed order by
+        // the down-projection -> the statistics (and the loss) are bit-reproducible run to run
         if (row_ok && !(sub & 1)) {
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row), "f"(s1) : "memory");
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.ff_rowsum + 2ll * row + 1), "f"(s2) : "memory");
+          const int nparts = p.ff_hidden >> 6;                     // 4d / 64 boxes per row
+          *reinterpret_cast<float2*>(p.ff_rowsum + 2ll * ((long long)row * nparts + n_blk * 2 + bs)) =
+              make_float2(s1, s2);
         }
       } else if constexpr (EPI == PEPI_FF_BWD) {
         // tile columns = hidden units [256 n_blk, +256).  16 warps: sub = warp>>2; half = sub>>1 owns
@@ -395,9 +398,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float invD = 1.f / (float)p.ff_hidden;
         float mean = 0.f, rstd = 0.f;
         if (row_ok) {
-          const float2 ss = *reinterpret_cast<const float2*>(p.ff_rowsum + 2ll * row);
-          mean = ss.x * invD;
-          rstd = rsqrtf(fmaxf(ss.y * invD - mean * mean, 0.f) + p.ff_eps);
+          const int nparts = p.ff_hidden >> 6;
+          const float4* parts = reinterpret_cast<const float4*>(p.ff_rowsum + 2ll * (long long)row * nparts);
+          float sx = 0.f, sy = 0.f;
+          for (int k = 0; k < nparts / 2; ++k) {                   // fixed order
+            const float4 v = __ldg(parts + k);
+            sx += v.x; sy += v.y; sx += v.z; sy += v.w;
+          }
+          mean = sx * invD;
+          rstd = rsqrtf(fmaxf(sy * invD - mean * mean, 0.f) + p.ff_eps);
           if (n_blk == 0) *reinterpret_cast<float2*>(p.ff_stats + 2ll * row) = make_float2(mean, rstd);
         }
         const bf16* res_row = (p.residual != nullptr && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;

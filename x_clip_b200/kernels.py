@@ -304,13 +304,13 @@ def ff_weights(w1, w2, g4):
 
 
 def ff_up(x, w1p, need_u=True):
-    """x bf16 [M,d] -> (u bf16 [M,8d] = [value|gate] or None, hp bf16 [M,4d], rowsum f32 [M,2]).
+    """x bf16 [M,d] -> (u bf16 [M,8d] = [value|gate] or None, hp bf16 [M,4d], rowsum f32 [M,d/16,2]).
     need_u=False (forward-only sweeps) skips the 8d-wide store of u."""
     _need(x, BF16, "x"); _rows2d(x, "x"); _need(w1p, BF16, "w1p")
     M, d = x.shape
     u = torch.empty((M, 8 * d), device=x.device, dtype=BF16) if need_u else None
     hp = torch.empty((M, 4 * d), device=x.device, dtype=BF16)
-    rowsum = torch.zeros((M, 2), device=x.device, dtype=F32)
+    rowsum = torch.empty((M, d // 16, 2), device=x.device, dtype=F32)    # one slot per 64-column box
     _call(x, "ff_up", 2.0 * M * 8 * d * d, 2.0 * (M * d + 8 * d * d + M * (12 if need_u else 4) * d), "xclip_ff_up",
           x.data_ptr(), x.stride(0), w1p.data_ptr(), _ptr(u), u.stride(0) if need_u else 0, hp.data_ptr(),
           hp.stride(0), rowsum.data_ptr(), M, d)
