@@ -36,8 +36,7 @@ def test_unknown_kwargs_swallowed_and_asserts_kept():
         x_clip_b200.CLIP(**TINY, text_causal_mask=True)          # eos id missing (x_clip.py:480)
 
 
-@pytest.mark.parametrize("kw", [dict(use_mlm=True), dict(use_visual_ssl=True),
-                                dict(text_dim_head=32), dict(dim_text=320), dict(sim_reg_loss_weight=0.1),
+@pytest.mark.parametrize("kw", [dict(text_dim_head=32), dict(dim_text=320), dict(sim_reg_loss_weight=0.1),
                                 dict(downsample_image_embeds=True, use_all_token_embeds=True),
                                 # rotary + causal is broken in the reference itself (x_clip.py:328)
                                 dict(text_causal_mask=True, text_eos_id=1, text_rotary_pos_emb=True),
@@ -46,6 +45,13 @@ def test_unknown_kwargs_swallowed_and_asserts_kept():
 def test_unsupported_flags_raise_at_construction(kw):
     with pytest.raises(x_clip_b200.Unsupported):
         x_clip_b200.CLIP(**{**TINY, **kw})
+
+
+def test_aux_loss_heads_construct_on_the_fast_encoders():
+    """use_mlm / use_visual_ssl wrap the SAME encoder modules (reference x_clip.py:516-552)."""
+    clip = x_clip_b200.CLIP(**TINY, use_mlm=True, use_visual_ssl=True)
+    assert clip.mlm.transformer is clip.text_transformer
+    assert clip.text_ssl_loss_weight == 0.05 and clip.image_ssl_loss_weight == 0.05
 
 
 def test_rotary_and_causal_towers_mirror_the_reference_parameter_tree():
