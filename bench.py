@@ -76,6 +76,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU (default: 4096 cfg3, 1024 cfg2)")
     ap.add_argument("--microbatch", type=int, default=None,
                     help="encoder micro-batch of the GradCache-style step (default: 512 cfg3, off cfg2)")
+    ap.add_argument("--retain", default="auto",
+                    help="micro-batched step: chunks whose activations stay resident in HBM between the "
+                         "forward and the backward sweep ('auto' = as many as fit, 0 = pure two-pass step)")
     ap.add_argument("--patch-dropout", type=float, default=0.5)
     ap.add_argument("--loss", default="nce", choices=sorted(LOSS_KW))
     ap.add_argument("--grad-sync", action="store_true",
@@ -89,6 +92,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg2 / cfg4 / cfg5 side measurements")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 per-rank parity check")
     a = ap.parse_args()
+    a.retain = a.retain if a.retain == "auto" else int(a.retain)
     d = DEFAULTS[a.workload]
     if a.batch is None:
         a.batch = d["batch"] if a.loss == "nce" else {"filip": 256, "dcl_extra": 8192}[a.loss]
@@ -97,11 +101,16 @@ def parse():
     return a
 
 
-def workload_text(args, batch=None):
+def workload_text(args, batch=None, plan=None):
     cfg, txt = WORKLOADS[args.workload]
     s = txt.format(b=batch or args.batch, pd=args.patch_dropout, loss=LOSS_TXT[args.loss])
     if args.microbatch:
-        s += f", encoder micro-batch {args.microbatch} (two-pass GradCache step: +1 encoder forward)"
+        s += f", encoder micro-batch {args.microbatch} (GradCache-style step"
+        if plan:
+            s += (f": activations of {plan['retained']} of {plan['chunks']} chunks stay in HBM, the other "
+                  f"{plan['chunks'] - plan['retained']} are re-encoded in backward = +{plan['chunks'] - plan['retained']}"
+                  f"/{plan['chunks']} encoder forward")
+        s += ")"
     return s
 
 
@@ -250,14 +259,14 @@ class Runner:
     (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks)."""
 
     def __init__(self, model_cfg, loss, batch, microbatch, patch_dropout, dev, rank, world, grad_sync=False,
-                 host_buffers=0):
+                 host_buffers=0, retain="auto"):
         import torch
         import x_clip_b200
         self.torch, self.dev, self.rank, self.world, self.B = torch, dev, rank, world, batch
         self.cfg = model_cfg
         torch.manual_seed(0)
         self.clip = x_clip_b200.CLIP(**model_cfg, **LOSS_KW[loss], visual_patch_dropout=patch_dropout,
-                                     microbatch=microbatch or None).to(dev)
+                                     microbatch=microbatch or None, microbatch_retain=retain).to(dev)
         self.clip.train()
         self.params = list(self.clip.parameters())
         self.host = []
@@ -461,7 +470,7 @@ def main():
     model_cfg, _ = WORKLOADS[args.workload]
     B = args.batch
     run = Runner(model_cfg, args.loss, B, args.microbatch, args.patch_dropout, dev, rank, world,
-                 grad_sync=args.grad_sync, host_buffers=0 if args.no_e2e else 2)
+                 grad_sync=args.grad_sync, host_buffers=0 if args.no_e2e else 2, retain=args.retain)
     note("model + data ready")
 
     # ---- (1) device-resident timing
@@ -482,6 +491,8 @@ def main():
     ms_dev = run.max_over_ranks(e0.elapsed_time(e1))
     launches = lib.xclip_launch_count()
     last_loss = loss.item()
+    plan = getattr(run.clip, "last_step_plan", None) if args.microbatch else None
+    peak_mem = torch.cuda.max_memory_allocated(dev)
     clocks = sampler.stop() if rank == 0 else None
     note(f"device-resident timing done: {ms_dev / args.steps:.1f} ms/step")
 
@@ -671,8 +682,9 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_text(args), "global_batch": Bg,
+        "config": {"workload": workload_text(args, plan=plan), "global_batch": Bg,
                    "global_batch_at_8_gpus": B * 8,
+                   "step_plan": plan, "peak_hbm_bytes_allocated": int(peak_mem),
                    "parallelism": f"dp{world}" + ("+grad-allreduce" if args.grad_sync and world > 1 else ""),
                    "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed",
                    "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks",

@@ -217,12 +217,18 @@ def test_microbatched_step_equals_single_pass(cuda_device):
     text, image = O.protocol_inputs(cfg, 6, 4321, 0.2)
     text, image = text.to(cuda_device), image.to(cuda_device)
     res = []
-    for mb in (None, 2, 4):
-        clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0., microbatch=mb).to(cuda_device)
+    # (micro-batch, retained chunks): none kept = pure two-pass step, some / all kept, planner
+    for mb, keep in ((None, 0), (2, 0), (4, 0), (2, 1), (2, 3), (2, "auto")):
+        clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0., microbatch=mb,
+                                microbatch_retain=keep).to(cuda_device)
         clip.load_state_dict(state)
         clip.train()
         loss = clip(text, image, return_loss=True)
         loss.backward()
+        if mb is not None:
+            plan = clip.last_step_plan
+            want = {0: 0, 1: 1, 3: 3, "auto": plan["chunks"]}[keep]       # tiny model: everything fits
+            assert plan["retained"] == want and plan["chunks"] == -(-6 // mb), plan
         res.append((loss.item(), {k: p.grad.clone() for k, p in clip.named_parameters() if p.grad is not None}))
     for loss, grads in res[1:]:
         assert abs(loss - res[0][0]) < 1e-5
@@ -232,19 +238,22 @@ def test_microbatched_step_equals_single_pass(cuda_device):
             assert (g - ref).norm().item() <= 2e-2 * ref.norm().item() + 1e-6, k
 
     # with patch dropout the per-chunk RNG is replayed in the recompute pass: deterministic, finite
+    # (same draw whether a chunk's activations were kept or it is re-encoded: retain 0 / 1 / all agree)
     clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0.5, microbatch=2).to(cuda_device)
     clip.load_state_dict(state)
     clip.train()
     out = []
-    for _ in range(2):
+    for keep in (0, 0, 1, "auto"):
+        clip.microbatch_retain = keep
         torch.manual_seed(7)
         for p in clip.parameters():
             p.grad = None
         loss = clip(text, image, return_loss=True)
         loss.backward()
         out.append((loss.item(), clip.to_visual_latent.weight.grad.clone()))
-    assert out[0][0] == out[1][0] and torch.isfinite(out[0][1]).all()      # the forward is bit-reproducible
-    assert (out[0][1] - out[1][1]).abs().max().item() <= 1e-3 * out[0][1].abs().max().item()
+    for o in out[1:]:
+        assert out[0][0] == o[0] and torch.isfinite(o[1]).all()      # the forward is bit-reproducible
+        assert (out[0][1] - o[1]).abs().max().item() <= 1e-3 * out[0][1].abs().max().item()
 
 
 def test_pluggable_encoders_freeze_and_maskless(cuda_device):

@@ -123,7 +123,7 @@ def test_constructor_and_forward_signatures_match_the_reference():
         if v is not inspect.Parameter.empty:
             assert our_init[k] == v, f"default of {k}: reference {v!r}, here {our_init[k]!r}"
     extra = sorted(set(our_init) - set(ref_init))
-    assert extra == ["microbatch"], f"unexpected extra constructor keywords: {extra}"
+    assert extra == ["microbatch", "microbatch_retain"], f"unexpected extra constructor keywords: {extra}"
     ref_fwd, our_fwd = params(ref.CLIP.forward), params(x_clip_b200.CLIP.forward)
     assert list(ref_fwd) == list(our_fwd), (list(ref_fwd), list(our_fwd))
     assert ref_fwd == our_fwd

@@ -308,6 +308,7 @@ class CLIP(nn.Module):
         checkpoint_during_training=False,
         sim_reg_loss_weight=0.,
         microbatch=None,   # (extension) encoder micro-batch for the GradCache-style large-batch step
+        microbatch_retain="auto",   # (extension) chunks whose activations stay in HBM: "auto" | int
         **kwargs,     # unknown keywords are swallowed, like the reference (:455)
     ):
         super().__init__()
@@ -385,6 +386,9 @@ class CLIP(nn.Module):
 
         self.multiview_loss_weight = multiview_loss_weight
         self.microbatch = microbatch
+        assert microbatch_retain == "auto" or (isinstance(microbatch_retain, int) and microbatch_retain >= 0)
+        self.microbatch_retain = microbatch_retain
+        self.last_step_plan = None      # filled by engine.ChunkedClipLossFn: chunks / retained / bytes
         # latched at construction, like the reference (:591): the process group must exist first
         self.requires_all_gather = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.sim_reg_loss_weight = sim_reg_loss_weight
@@ -480,7 +484,7 @@ class CLIP(nn.Module):
         if (return_loss and self.microbatch and text.shape[0] > self.microbatch and not has_aux
                 and not self.use_all_token_embeds and not (freeze_image_encoder or freeze_text_encoder)):
             return E.ChunkedClipLossFn.apply(self, text, image, text_mask, int(self.microbatch),
-                                             self.temperature)
+                                             self.temperature, self.microbatch_retain)
         text_args = (text,) if self.text_encode_without_mask else (text, text_mask)
         enc_text = _encode(self.text_transformer, text_args, freeze_text_encoder)
         if self.text_causal_mask:

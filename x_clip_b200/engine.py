@@ -451,27 +451,71 @@ def _pad_rows(m: torch.Tensor, rows: int) -> torch.Tensor:
     return out
 
 
+def _avail_bytes(dev) -> int:
+    """HBM a further allocation can draw on: free device memory + the cached-but-unused part of
+    torch's pool (counted at 80 %: cached blocks are not one contiguous range)."""
+    free, _ = torch.cuda.mem_get_info(dev)
+    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    return int(free + 0.8 * max(cached, 0))
+
+
+# HBM head-room the retention planner leaves untouched: contrastive-loss workspace (g[b, B_g] bf16
+# per direction, gathered operands), gradient buckets, allocator slack.
+RETAIN_MARGIN_BYTES = 10 << 30
+# transient buffers of one chunk's backward (du 8d + a few d-wide rows of one layer) relative to
+# the chunk's saved activations (22 d per token-layer x depth)
+RETAIN_TRANSIENT_FRAC = 0.15
+
+
 class ChunkedClipLossFn(torch.autograd.Function):
-    """Full-batch contrastive loss with micro-batched encoders (memory: one chunk of activations).
+    """Full-batch contrastive loss with micro-batched encoders.
 
     The reference offers `checkpoint_during_training` (x_clip.py:280-286) to fit large batches;
     here the same need (4096 pairs per GPU for a 32768 global batch) is met by a GradCache-style
     schedule that is mathematically identical to the single-pass step:
-      1. encode every chunk without saving activations -> latents of the whole local batch
+      1. encode every chunk -> latents of the whole local batch
       2. one contrastive loss over ALL latents (with the usual cross-rank all-gather)
-      3. in backward: d loss / d latents, then re-encode chunk by chunk with activations saved
-         and back-propagate the matching slice of the latent gradient into the parameters.
-    RNG (PatchDropout) is replayed per chunk.  Costs one extra encoder forward (4/3 x flops)."""
+      3. in backward: d loss / d latents, then back-propagate the matching slice of the latent
+         gradient through every chunk's encoders.
+    B200-first memory plan: a chunk's saved activations are KEPT from step 1 for as many chunks as
+    the 180 GB of HBM hold (`retain`: "auto" measures the first chunk's footprint and plans against
+    the free memory; an int fixes the count; 0 = none); only the remaining chunks are encoded
+    without saving anything and re-encoded in step 3 (RNG replayed for PatchDropout).  Retained
+    chunks cost no extra flops; each re-encoded chunk costs one extra encoder forward."""
 
     @staticmethod
-    def forward(ctx, clip, text, image, text_mask, chunk, temperature):
+    def forward(ctx, clip, text, image, text_mask, chunk, temperature, retain="auto"):
         B = text.shape[0]
+        dev = text.device
         bounds = [(s, min(s + chunk, B)) for s in range(0, B, chunk)]
-        rng_states, zs, opss = [], [], []
+        rng_states, zs, opss, kept = [], [], [], []
+        foot = None                                   # bytes of one retained chunk's activations
         with torch.no_grad(), weight_scope():
-            for s, e in bounds:
-                rng_states.append(torch.cuda.get_rng_state(text.device))
-                z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+            for k, (s, e) in enumerate(bounds):
+                rng_states.append(torch.cuda.get_rng_state(dev))
+                if retain == "auto":
+                    scale = (e - s) / float(chunk)
+                    if foot is None:                  # first chunk: keep it, measure it
+                        keep_it = True
+                    else:
+                        need = foot * scale * (1.0 + RETAIN_TRANSIENT_FRAC) + RETAIN_MARGIN_BYTES
+                        keep_it = _avail_bytes(dev) >= need
+                else:
+                    keep_it = k < int(retain)
+                if keep_it:
+                    before = torch.cuda.memory_allocated(dev)
+                    with torch.enable_grad():
+                        z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                    kept.append(list(z))
+                    if foot is None:
+                        foot = max(torch.cuda.memory_allocated(dev) - before, 1)
+                        if retain == "auto" and len(bounds) > 1 and \
+                                _avail_bytes(dev) < foot * (1.0 + RETAIN_TRANSIENT_FRAC) + RETAIN_MARGIN_BYTES:
+                            kept[-1] = None           # not even a second live chunk fits beside it: let it go
+                    z = [t.detach() for t in z]
+                else:
+                    z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                    kept.append(None)
                 zs.append(z)
                 opss.append(ops)
         nsets = len(zs[0])
@@ -485,8 +529,10 @@ class ChunkedClipLossFn(torch.autograd.Function):
                 leaves[3] if nsets == 4 else None, temp_leaf, ops_all,
                 clip.decoupled_contrastive_learning, clip.requires_all_gather)
         ctx.clip, ctx.inputs = clip, (text, image, text_mask)
-        ctx.bounds, ctx.rng_states = bounds, rng_states
+        ctx.bounds, ctx.rng_states, ctx.kept = bounds, rng_states, kept
         ctx.graph = (loss, leaves, temp_leaf)
+        clip.last_step_plan = dict(chunks=len(bounds), retained=sum(z is not None for z in kept),
+                                   chunk_activation_bytes=foot)
         return loss.detach()
 
     @staticmethod
@@ -499,16 +545,24 @@ class ChunkedClipLossFn(torch.autograd.Function):
         dz = [l.grad for l in leaves]
         dev = text.device
         keep_state = torch.cuda.get_rng_state(dev)
-        last = len(ctx.bounds) - 1
+        kept = ctx.kept
+        # retained chunks first: their backward releases HBM before any chunk is re-encoded
+        order = [k for k in range(len(ctx.bounds)) if kept[k] is not None] + \
+                [k for k in range(len(ctx.bounds)) if kept[k] is None]
         with weight_scope():
-            for k, ((s, e), st) in enumerate(zip(ctx.bounds, ctx.rng_states)):
-                torch.cuda.set_rng_state(st, dev)
+            for pos, k in enumerate(order):
+                s, e = ctx.bounds[k]
                 # parameter gradients accumulate over the chunks; gradient-sync hooks (GradSync)
                 # must see a parameter ONCE per step, with its complete gradient: every chunk but
-                # the last runs with the hooks deferred (the DDP no_sync convention)
-                with torch.enable_grad(), D_.defer_grad_sync(k != last):
-                    z, _ = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                # the last one processed runs with the hooks deferred (the DDP no_sync convention)
+                with torch.enable_grad(), D_.defer_grad_sync(pos != len(order) - 1):
+                    if kept[k] is not None:
+                        z, kept[k] = kept[k], None
+                    else:
+                        torch.cuda.set_rng_state(ctx.rng_states[k], dev)
+                        z, _ = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
                     torch.autograd.backward(list(z), [d[s:e] for d in dz])   # accumulates into .grad
+                    del z
         torch.cuda.set_rng_state(keep_state, dev)
-        ctx.graph = ctx.inputs = None
-        return None, None, None, None, None, temp_leaf.grad
+        ctx.graph = ctx.inputs = ctx.kept = None
+        return None, None, None, None, None, temp_leaf.grad, None
