@@ -79,6 +79,7 @@ def parse():
     ap.add_argument("--retain", default="auto",
                     help="micro-batched step: chunks whose activations stay resident in HBM between the "
                          "forward and the backward sweep ('auto' = as many as fit, 0 = pure two-pass step)")
+    ap.add_argument("--tune", default="", help="A/B switches 'knob=value,...' passed to xclip_tune_set")
     ap.add_argument("--patch-dropout", type=float, default=0.5)
     ap.add_argument("--loss", default="nce", choices=sorted(LOSS_KW))
     ap.add_argument("--grad-sync", action="store_true",
@@ -461,6 +462,9 @@ def main():
     from x_clip_b200 import _lib, kernels
     lib = _lib.load()
     _lib.call("xclip_init")
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        lib.xclip_tune_set(int(k), int(v))
 
     parity = None
     if world > 1 and not args.no_parity:

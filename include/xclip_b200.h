@@ -45,6 +45,13 @@ int xclip_init(void);
 /* number of kernels this library has launched since the last reset (host counter) */
 long long xclip_launch_count(void);
 void xclip_launch_count_reset(void);
+/* Explicit, process-wide tuning switches for A/B measurements (never read from the environment;
+ * results are identical either way).  Returns the previous value, -1 for an unknown knob.
+ *   XCLIP_TUNE_FF_BWD_PREFETCH (0): xclip_ff_bwd pulls the next tile's u blocks towards L2 (default 1)
+ *   XCLIP_TUNE_ATTN_SMALL_CTAS (1): resident CTAs per SM of the n <= 128 attention forward, 0 = built-in */
+#define XCLIP_TUNE_FF_BWD_PREFETCH 0
+#define XCLIP_TUNE_ATTN_SMALL_CTAS 1
+int xclip_tune_set(int knob, int value);
 
 /* ---- dense contraction (tcgen05) --------------------------------------
  * C[M,N] (+)= alpha * A * B^T (+ bias[N]) (+ residual[res_row_idx[row] | row % res_row_mod | row, N])

@@ -29,6 +29,7 @@ SIGNATURES = {
     "xclip_launch_count": (c_longlong, []),
     "xclip_launch_count_reset": (None, []),
     "xclip_gemm_set_pair_mode": (c_int, [c_int]),
+    "xclip_tune_set": (c_int, [c_int, c_int]),
     "xclip_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
                                 c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_int64, c_int, c_void_p, c_int, c_void_p]),

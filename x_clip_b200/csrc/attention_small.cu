@@ -352,7 +352,9 @@ static int launch_fwd_small(const void* qkv, int64_t ld_qkv, const AttnSmallFwdP
   auto kern = attn_fwd_small_kernel<ROWS, kCausal>;
   rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), kSmem);
   if (rc) return rc;
-  long long grid = (long long)num_sms() * kPerSm;
+  int per_sm = tune(XCLIP_TUNE_ATTN_SMALL_CTAS);          // A/B switch: fewer co-resident CTAs
+  if (per_sm <= 0 || per_sm > kPerSm) per_sm = kPerSm;
+  long long grid = (long long)num_sms() * per_sm;
   if (grid > (long long)p.B * p.H) grid = (long long)p.B * p.H;
   kern<<<(int)grid, kThreads, kSmem, stream>>>(tm, p);
   XCLIP_LAUNCH_CHECK("attn_fwd_small_kernel");

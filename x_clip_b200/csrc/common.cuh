@@ -361,5 +361,79 @@ __device__ __forceinline__ GeluParts gelu_parts(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 
+// ---------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100: FFMA2 - one instruction, one issue slot, two IEEE fp32 FMAs on
+// an aligned register pair).  The GELU epilogues of the fused feed-forward are bound by the FMA pipe
+// (~28 FMA-class instructions per element in scalar form against 2 MUFU); in packed form the
+// polynomial and the affine chains cost half the instructions and the two MUFU become the floor.
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// two consecutive bf16 of one 32-bit word -> packed fp32 pair (element 0 in the low half)
+__device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t w) {
+  return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+
+// gelu_parts for two elements at once: cdf = Phi(x), pdf = phi(x) (same A&S 7.1.26 polynomial).
+struct GeluParts2 {
+  f32x2 cdf, pdf;
+};
+__device__ __forceinline__ GeluParts2 gelu_parts2(float x0, float x1) {
+  const f32x2 x = f2_pack(x0, x1);
+  const f32x2 z = f2_mul(f2_pack(fabsf(x0), fabsf(x1)), f2_splat(0.70710678118654752f));
+  float d0, d1, t0, t1;
+  f2_unpack(f2_fma(f2_splat(0.3275911f), z, f2_splat(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const f32x2 t = f2_pack(t0, t1);
+  f32x2 poly = f2_fma(f2_splat(1.061405429f), t, f2_splat(-1.453152027f));
+  poly = f2_fma(poly, t, f2_splat(1.421413741f));
+  poly = f2_fma(poly, t, f2_splat(-0.284496736f));
+  poly = f2_fma(poly, t, f2_splat(0.254829592f));
+  poly = f2_mul(poly, t);
+  float a0, a1, e0, e1;
+  f2_unpack(f2_mul(f2_mul(x, f2_splat(-0.72134752044448170f)), x), a0, a1);     // -x^2/2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 e_half = f2_pack(e0, e1);
+  // q = 0.5 - 0.5 erfc(|x|/sqrt2) >= 0;  Phi(x) = 0.5 + sign(x) q
+  float q0, q1;
+  f2_unpack(f2_fma(f2_mul(poly, e_half), f2_splat(-0.5f), f2_splat(0.5f)), q0, q1);
+  q0 = __uint_as_float(__float_as_uint(q0) | (__float_as_uint(x0) & 0x80000000u));
+  q1 = __uint_as_float(__float_as_uint(q1) | (__float_as_uint(x1) & 0x80000000u));
+  GeluParts2 g;
+  g.cdf = f2_add(f2_pack(q0, q1), f2_splat(0.5f));
+  g.pdf = f2_mul(e_half, f2_splat(0.3989422804014327f));
+  return g;
+}
+
 
 }  // namespace xclip

@@ -224,6 +224,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int split = t / (num_n * num_m2);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if constexpr (EPI == PEPI_FF_BWD) {
+        // The epilogue reads 256 KiB of u per tile pair and is the longest phase of this kernel: start
+        // the NEXT tile's u blocks on their way to L2 now (no registers held; 512 epilogue threads,
+        // one 128-byte line of the value half and one of the gate half each).
+        const int tn = t + npairs;
+        if (p.ff_prefetch && tn < num_tiles) {
+          const int tmn2 = tn % (num_n * num_m2);
+          const int rr = ((tmn2 / num_n) * 2 + (int)rank) * kGemmBlockM + (threadIdx.x >> 2);
+          if (rr < p.M) {
+            const bf16* src = p.ff_u + (long long)rr * p.ff_ldu + (tmn2 % num_n) * BLOCK_N + (threadIdx.x & 3) * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + p.ff_hidden));
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
@@ -242,7 +257,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // All arithmetic happens BEFORE the staging boxes are touched: the results wait in registers
         // (48 packed words) while the previous tile's TMA stores are still draining the boxes, so the
         // store latency overlaps the TMEM reads and the GELU math instead of serialising with them.
+        // (packed fp32x2 arithmetic: two columns per instruction, see common.cuh)
         float s1 = 0.f, s2 = 0.f;
+        f32x2 s1p = f2_splat(0.f), s2p = f2_splat(0.f);
         uint32_t pv[16], pg[16], ph[16];
 #pragma unroll
         for (int c16 = 0; c16 < 2; ++c16) {
@@ -252,18 +269,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            float hp2[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float va = __uint_as_float(vv[i + e]), ga = __uint_as_float(gg[i + e]);
-              hp2[e] = bf16_rn(va * gelu_erf(ga));        // statistics of what the next GEMM reads
-              s1 += hp2[e];
-              s2 = fmaf(hp2[e], hp2[e], s2);
-            }
-            pv[c16 * 8 + (i >> 1)] = pack_bf16x2(__uint_as_float(vv[i]), __uint_as_float(vv[i + 1]));
-            pg[c16 * 8 + (i >> 1)] = pack_bf16x2(__uint_as_float(gg[i]), __uint_as_float(gg[i + 1]));
-            ph[c16 * 8 + (i >> 1)] = pack_bf16x2(hp2[0], hp2[1]);
+            const float va0 = __uint_as_float(vv[i]), va1 = __uint_as_float(vv[i + 1]);
+            const float ga0 = __uint_as_float(gg[i]), ga1 = __uint_as_float(gg[i + 1]);
+            const GeluParts2 gp = gelu_parts2(ga0, ga1);
+            const f32x2 ge = f2_mul(f2_pack(ga0, ga1), gp.cdf);               // gelu(gate)
+            const uint32_t hw = f2_to_bf16x2(f2_mul(f2_pack(va0, va1), ge));    // hp, rounded to bf16
+            const f32x2 hr = f2_from_bf16x2(hw);           // statistics of what the next GEMM reads
+            s1p = f2_add(s1p, hr);
+            s2p = f2_fma(hr, hr, s2p);
+            pv[c16 * 8 + (i >> 1)] = pack_bf16x2(va0, va1);
+            pg[c16 * 8 + (i >> 1)] = pack_bf16x2(ga0, ga1);
+            ph[c16 * 8 + (i >> 1)] = hw;
           }
+        }
+        {
+          float a, b;
+          f2_unpack(s1p, a, b); s1 = a + b;
+          f2_unpack(s2p, a, b); s2 = a + b;
         }
         // the accumulator is in registers now: hand the TMEM buffer back to the MMA warp at once
         tcgen05_fence_before();
@@ -327,6 +349,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float2 ab = *reinterpret_cast<const float2*>(p.ff_ab + 2ll * row);
           mean = st.x; rstd = st.y; am = ab.x; bm = ab.y;
         }
+        const f32x2 rstd2 = f2_splat(rstd), nmr = f2_splat(-mean * rstd), namr = f2_splat(-am * rstd),
+                    nbmr = f2_splat(-bm * rstd);
         const int slab_row0 = m_blk * kGemmBlockM + quarter * 32;      // first global row of the slab
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
@@ -367,21 +391,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(stg + off));
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(wg[0]), "=r"(wg[1]), "=r"(wg[2]), "=r"(wg[3]) : "r"(stg + S::kBox + off));
-              float dv[8], dg[8];
+              uint32_t dvw[4], dgw[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float2 pv = unpack_bf16x2(wv[e >> 1]), pg = unpack_bf16x2(wg[e >> 1]);
-                const float val = (e & 1) ? pv.y : pv.x, gate = (e & 1) ? pg.y : pg.x;
-                const GeluParts gp = gelu_parts(gate);
-                const float ge = gate * gp.cdf;                       // gelu(gate)
-                const float gd = fmaf(gate, gp.pdf, gp.cdf);          // gelu'(gate)
-                const float hn = (val * ge - mean) * rstd;
-                const float dhp = rstd * (__uint_as_float(v[i + e]) - am - hn * bm);
-                dv[e] = dhp * ge;
-                dg[e] = dhp * val * gd;
+              for (int k = 0; k < 4; ++k) {                           // two columns per step (fp32x2)
+                const float g0 = __uint_as_float(wg[k] << 16), g1 = __uint_as_float(wg[k] & 0xffff0000u);
+                const f32x2 gate = f2_pack(g0, g1), val = f2_from_bf16x2(wv[k]);
+                const GeluParts2 gp = gelu_parts2(g0, g1);
+                const f32x2 ge = f2_mul(gate, gp.cdf);                // gelu(gate)
+                const f32x2 gd = f2_fma(gate, gp.pdf, gp.cdf);        // gelu'(gate)
+                const f32x2 hn = f2_fma(f2_mul(val, ge), rstd2, nmr); // (val*ge - mean) rstd
+                f32x2 dhp = f2_fma(f2_pack(__uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1])),
+                                   rstd2, namr);                      // rstd (gdh - a)
+                dhp = f2_fma(hn, nbmr, dhp);                          //   - rstd b hn
+                dvw[k] = f2_to_bf16x2(f2_mul(dhp, ge));
+                dgw[k] = f2_to_bf16x2(f2_mul(f2_mul(dhp, val), gd));
               }
-              st_box_bf16x8(stg, row_in_tile, chunk, dv);
-              st_box_bf16x8(stg + S::kBox, row_in_tile, chunk, dg);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(dvw[0]),
+                           "r"(dvw[1]), "r"(dvw[2]), "r"(dvw[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(dgw[0]),
+                           "r"(dgw[1]), "r"(dgw[2]), "r"(dgw[3]) : "memory");
             }
           }
           fence_proxy_async_smem();
