@@ -34,6 +34,7 @@ struct AttnSmallFwdParams {
   bf16* o;
   long long ldo;
   float* lse;              // [B, H, n] base-2 log-sum-exp of the scaled, masked scores
+  int prefetch;            // A/B: pull the CTA's next item towards L2 while this one is computed
 };
 
 __device__ __forceinline__ float sm_ex2(float x) {
@@ -176,6 +177,15 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
         tma_load_3d(sK, &tm_qkv, qk_bar, inner + h * kSDh, 0, b);
         mbar_arrive_expect_tx(v_bar, kBox);
         tma_load_3d(sV, &tm_qkv, v_bar, 2 * inner + h * kSDh, 0, b);
+        if (p.prefetch) {   // the CTA's NEXT item travels HBM -> L2 while this one is computed
+          const int bh2 = bh + (int)gridDim.x;
+          if (bh2 < total) {
+            const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+            tma_prefetch_l2_3d(&tm_qkv, h2 * kSDh, 0, b2);
+            tma_prefetch_l2_3d(&tm_qkv, inner + h2 * kSDh, 0, b2);
+            tma_prefetch_l2_3d(&tm_qkv, 2 * inner + h2 * kSDh, 0, b2);
+          }
+        }
         if (it > 0) mbar_wait(e_bar, par ^ 1);   // O of the previous item was read out of TMEM
         mbar_wait(qk_bar, par);
         tcgen05_fence_after();
@@ -232,7 +242,43 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
       mbar_wait(s_bar, par);
       tcgen05_fence_after();
       float m2 = -INFINITY, sum = 0.f;
-      if (alive) {
+      if (alive && fast) {
+        // ---- table-free path (no masked key, not causal): the scale is positive, so the row maximum is
+        // taken over the RAW scores (one FMNMX per element) and scaled once; pass 2 is one FFMA + one
+        // MUFU.EX2 per element:  p = 2^(raw * c - m2)
+        float mr = -INFINITY;
+        for (int c0 = 0; c0 < p.nkp; c0 += 16) {         // (16-column steps: nkp is a multiple of 16)
+          const int valid = p.n - c0;
+          uint32_t w[16];
+          tmem_ld_32x16(t_row + c0, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (valid >= 16 || i < valid) mr = fmaxf(mr, __uint_as_float(w[i]));
+        }
+        m2 = mr * c;
+        const float nm2 = -m2;
+        for (int c0 = 0; c0 < p.nkp; c0 += 16) {
+          const int valid = p.n - c0;
+          uint32_t w[16];
+          tmem_ld_32x16(t_row + c0, w);
+          tmem_ld_wait();
+          const uint32_t blk = smem_u32(sQ) + (c0 >> 6) * kPBlk;
+          const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = sm_ex2(fmaf(__uint_as_float(w[cc * 8 + i]), c, nm2));
+              e[i] = (valid >= 16 || cc * 8 + i < valid) ? x : 0.f;
+            }
+            sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            sm_sts_v4(blk + swz128(row, chunk0 + cc), pack_bf16x2(e[0], e[1]),
+                      pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          }
+        }
+      } else if (alive) {
         // ---- pass 1: row maximum
         for (int c0 = 0; c0 < p.nkp; c0 += 32) {
           uint32_t v[32];
@@ -372,6 +418,7 @@ struct AttnSmallBwdParams {
   const float* delta;    // [B, H, n] rowsum(dO * O)
   bf16* dqkv;            // [B*n, ld]: dq | dk | dv
   long long ld;
+  int prefetch;          // A/B: next item towards L2 (see the forward kernel)
 };
 
 constexpr int kSBwdComputeWarps = 8;
@@ -471,6 +518,16 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv,
         mbar_arrive_expect_tx(vdo_bar, 2 * box);
         tma_load_3d(sP, &tm_qkv, vdo_bar, 2 * inner + h * kSDh, 0, b);
         tma_load_3d(sdO, &tm_do, vdo_bar, h * kSDh, 0, b);
+        if (p.prefetch) {
+          const int bh2 = bh + (int)gridDim.x;
+          if (bh2 < total) {
+            const int b2 = bh2 / p.H, h2 = bh2 - b2 * p.H;
+            tma_prefetch_l2_3d(&tm_qkv, h2 * kSDh, 0, b2);
+            tma_prefetch_l2_3d(&tm_qkv, inner + h2 * kSDh, 0, b2);
+            tma_prefetch_l2_3d(&tm_qkv, 2 * inner + h2 * kSDh, 0, b2);
+            tma_prefetch_l2_3d(&tm_do, h2 * kSDh, 0, b2);
+          }
+        }
         if (it > 0) mbar_wait(e_bar, par ^ 1);   // dQ/dK/dV of the previous item left TMEM
         mbar_wait(qk_bar, par);
         tcgen05_fence_after();
@@ -666,6 +723,7 @@ int attn_bwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, con
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.mask = key_mask; p.lse = lse; p.delta = delta;
   p.dqkv = reinterpret_cast<bf16*>(dqkv); p.ld = ld_dqkv;
+  p.prefetch = tune(XCLIP_TUNE_ATTN_SMALL_PREFETCH);
   CUtensorMap tq, tdo;
   int rc = encode_3d_bf16(&tq, qkv, (uint64_t)(3 * heads * kSDh), (uint64_t)n, (uint64_t)B,
                           (uint64_t)ld_qkv, (uint64_t)n * ld_qkv, kSDh, (uint32_t)p.nkp);
@@ -704,6 +762,7 @@ int attn_fwd_small(const void* qkv, int64_t ld_qkv, const uint8_t* key_mask, voi
   p.o = reinterpret_cast<bf16*>(o);
   p.ldo = ldo;
   p.lse = lse;
+  p.prefetch = tune(XCLIP_TUNE_ATTN_SMALL_PREFETCH);
   if (n <= 64)
     return causal ? launch_fwd_small<64, true>(qkv, ld_qkv, p, stream)
                   : launch_fwd_small<64, false>(qkv, ld_qkv, p, stream);

@@ -124,6 +124,25 @@ class _WgradStream:
             self.main.wait_stream(self.side)
 
 
+# Set by the micro-batched step for every chunk but the last one it back-propagates: transformer
+# weight gradients are then accumulated by the kernels straight INTO the existing `.grad` buffers
+# (split-K wgrad GEMM with accumulate, gain gradients by atomics) and `None` is returned to autograd -
+# no zero-filled temporary, no `grad += new` pass per parameter and chunk.  The last chunk returns
+# ordinary gradient tensors, so post-accumulate hooks (GradSync) fire exactly once per step.
+_accumulate_into_grad = False
+INPLACE_GRAD_ACCUMULATION = True     # module switch for A/B measurements (tools/ab_step.py)
+
+
+def _grad_target(param: torch.Tensor):
+    """`param.grad` when this backward may accumulate into it in place, else None."""
+    if not _accumulate_into_grad:
+        return None
+    g = getattr(param, "grad", None)
+    if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != param.shape or not param.is_leaf:
+        return None
+    return g
+
+
 class TransformerFn(torch.autograd.Function):
     """x[B,n,d] (bf16) -> norm_out(blocks(norm_in(x))) (bf16); mask: bool [B,n] or None.
 
@@ -208,9 +227,24 @@ class TransformerFn(torch.autograd.Function):
 
         grads: List[Optional[torch.Tensor]] = [None] * len(weights)
         wg = _WgradStream(dev)
-        dg_out = torch.zeros(d, device=dev, dtype=F32)
+
+        def gain_grad(idx):
+            """fp32 accumulator for the gain gradient of weights[idx]: its .grad (in-place mode) or zeros"""
+            tgt = _grad_target(weights[idx])
+            if tgt is not None:
+                return tgt, None
+            z = torch.zeros(weights[idx].shape[0], device=dev, dtype=F32)
+            return z, z
+
+        def weight_grad(idx, dy_, x_):
+            tgt = _grad_target(weights[idx])
+            if tgt is not None:
+                K.gemm(dy_, x_, a_major=1, b_major=1, out=tgt, accumulate=True)
+                return None
+            return wg.wgrad(dy_, x_)
+
+        dg_out, grads[1] = gain_grad(1)
         dx = K.layernorm_bwd(dout, x_last, st_out, g_out, dg=dg_out)
-        grads[1] = dg_out
         for L in reversed(range(depth)):
             g1, wqkv, wo, go, g2, w1, g4, w2 = layers[L]
             xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h = ctx.saved[L]
@@ -218,7 +252,7 @@ class TransformerFn(torch.autograd.Function):
             bqkv, bo, b1, b2 = ctx.wb[L]
             base = 2 + 8 * L
             # feed-forward: x2 = h @ w2^T + x1
-            dg4 = torch.zeros(g4.shape[0], device=dev, dtype=F32)
+            dg4, grads[base + 6] = gain_grad(base + 6)
             if ctx.fused_ff:
                 # h is the pre-norm hp.  Row means of the LayerNorm backward from d-wide data, the
                 # LN + GEGLU backward inside the dgrad GEMM, dW2 / dg4 from dW2g = dxs^T hp - vsum
@@ -226,37 +260,37 @@ class TransformerFn(torch.autograd.Function):
                 ctx.ff_saved[L] = None
                 dxs, vsum, ab = K.ff_bwd_prep(dx, st_v, acc, colvec)
                 du = K.ff_bwd(dx, w2g, u, st_v, ab)
-                grads[base + 7] = K.ff_w2_grad_post_(wg.wgrad(dxs, h), vsum, g4.detach(), w2.detach(), dg4)
+                dw2 = K.ff_w2_grad_post_(wg.wgrad(dxs, h), vsum, g4.detach(), w2.detach(), dg4)
+                tgt = _grad_target(w2)
+                if tgt is not None:
+                    tgt.add_(dw2)
+                    dw2 = None
+                grads[base + 7] = dw2
                 dh = None
             else:
                 dh = K.gemm(dx, b2, b_major=1)
-                grads[base + 7] = wg.wgrad(dx, h)
+                grads[base + 7] = weight_grad(base + 7, dx, h)
                 du = K.geglu_ln_bwd(dh, u, st_v, g4, dg=dg4)
-            grads[base + 6] = dg4
             del dh
             dxn2 = K.gemm(du, b1, b_major=1)
-            grads[base + 5] = wg.wgrad(du, xn2)
+            grads[base + 5] = weight_grad(base + 5, du, xn2)
             del du
-            dg2 = torch.zeros(d, device=dev, dtype=F32)
+            dg2, grads[base + 4] = gain_grad(base + 4)
             dx1 = K.layernorm_bwd(dxn2, x1, st_x1, g2, add=dx, dg=dg2)
-            grads[base + 4] = dg2
             # attention: x1 = LN(o @ wo^T) * go + x
-            dgo = torch.zeros(d, device=dev, dtype=F32)
+            dgo, grads[base + 3] = gain_grad(base + 3)
             dy = K.layernorm_bwd(dx1, y, st_y, go, dg=dgo)
-            grads[base + 3] = dgo
             d_o = K.gemm(dy, bo, b_major=1)
-            grads[base + 2] = wg.wgrad(dy, o)
+            grads[base + 2] = weight_grad(base + 2, dy, o)
             dqkv = K.attn_bwd(qkv, ctx.mask, o, d_o, lse, B, n, heads, scale, causal)
             if rot_cos is not None:      # back through the rotation (its transpose)
                 K.rotary_(dqkv, n, 3 * heads, rot_cos, rot_sin, inverse=True)
             dxn = K.gemm(dqkv, bqkv, b_major=1)
-            grads[base + 1] = wg.wgrad(dqkv, xn)
-            dg1 = torch.zeros(d, device=dev, dtype=F32)
+            grads[base + 1] = weight_grad(base + 1, dqkv, xn)
+            dg1, grads[base + 0] = gain_grad(base + 0)
             dx = K.layernorm_bwd(dxn, xcur, st1, g1, add=dx1, dg=dg1)
-            grads[base + 0] = dg1
-        dg_in = torch.zeros(d, device=dev, dtype=F32)
+        dg_in, grads[0] = gain_grad(0)
         dx_in = K.layernorm_bwd(dx, x_in, st_in, g_in, dg=dg_in)
-        grads[0] = dg_in
         wg.join()
         ctx.saved = ctx.wb = None
         return (dx_in.view(B, n, d), None, None, None, None, None, None, None, *grads)
@@ -467,6 +501,22 @@ RETAIN_MARGIN_BYTES = 10 << 30
 RETAIN_TRANSIENT_FRAC = 0.15
 
 
+class _InPlaceGradAccumulation:
+    def __init__(self, flag: bool):
+        self.flag = flag
+
+    def __enter__(self):
+        global _accumulate_into_grad
+        self.prev = _accumulate_into_grad
+        _accumulate_into_grad = self.flag
+        return self
+
+    def __exit__(self, *exc):
+        global _accumulate_into_grad
+        _accumulate_into_grad = self.prev
+        return False
+
+
 class ChunkedClipLossFn(torch.autograd.Function):
     """Full-batch contrastive loss with micro-batched encoders.
 
@@ -555,7 +605,8 @@ class ChunkedClipLossFn(torch.autograd.Function):
                 # parameter gradients accumulate over the chunks; gradient-sync hooks (GradSync)
                 # must see a parameter ONCE per step, with its complete gradient: every chunk but
                 # the last one processed runs with the hooks deferred (the DDP no_sync convention)
-                with torch.enable_grad(), D_.defer_grad_sync(pos != len(order) - 1):
+                with torch.enable_grad(), D_.defer_grad_sync(pos != len(order) - 1), \
+                        _InPlaceGradAccumulation(INPLACE_GRAD_ACCUMULATION and pos != len(order) - 1):
                     if kept[k] is not None:
                         z, kept[k] = kept[k], None
                     else:
