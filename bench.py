@@ -12,8 +12,9 @@ Default workload = cfg3 of BASELINE.json, the configuration the metric is quoted
 tower (dim 768, 12 layers, 12 heads, 224 px / patch 16, reference-default visual_patch_dropout 0.5)
 + 12-layer text tower (dim 512, 77 tokens), dim_latent 512, plain InfoNCE, 4096 pairs per GPU
 (global batch 4096*N: 32768 at N = 8, weak scaling, negatives all-gathered across ranks), encoder
-micro-batch 512 (GradCache-style two-pass step, engine.ChunkedClipLossFn: 4096 pairs of ViT-B/16
-activations do not fit 180 GB, the reference's own answer is activation checkpointing).
+micro-batch 768 (GradCache-style step, engine.ChunkedClipLossFn: 4096 pairs of ViT-B/16 activations are
+~260 GB; the chunks that fit the 180 GB of HBM keep their activations, the rest is re-encoded in backward;
+the reference's own answer is activation checkpointing).
 
 One JSON line on rank 0:
   value        pairs/s with the batch already on the device
@@ -44,6 +45,10 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# The micro-batched step keeps as many chunks of activations resident as the 180 GB of HBM hold and runs
+# within a few GB of the limit: torch's allocator must be able to re-map its cached memory instead of
+# fragmenting it (must be set before the first `import torch`; a user's own setting wins).
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 README_CFG = dict(dim_text=512, dim_image=512, dim_latent=512, num_text_tokens=10000,
                   text_enc_depth=6, text_seq_len=256, text_heads=8, visual_enc_depth=6,
@@ -63,7 +68,7 @@ LOSS_KW = {"nce": {}, "dcl_extra": dict(decoupled_contrastive_learning=True, ext
            "filip": dict(use_all_token_embeds=True)}
 LOSS_TXT = {"nce": "plain InfoNCE", "dcl_extra": "DCL + extra latent projection",
             "filip": "FILIP (use_all_token_embeds)"}
-DEFAULTS = {"cfg3": dict(batch=4096, microbatch=512), "cfg2": dict(batch=1024, microbatch=0)}
+DEFAULTS = {"cfg3": dict(batch=4096, microbatch=768), "cfg2": dict(batch=1024, microbatch=0)}
 
 
 def parse():
@@ -75,7 +80,7 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU (default: 4096 cfg3, 1024 cfg2)")
     ap.add_argument("--microbatch", type=int, default=None,
-                    help="encoder micro-batch of the GradCache-style step (default: 512 cfg3, off cfg2)")
+                    help="encoder micro-batch of the GradCache-style step (default: 768 cfg3, off cfg2)")
     ap.add_argument("--retain", default="auto",
                     help="micro-batched step: chunks whose activations stay resident in HBM between the "
                          "forward and the backward sweep ('auto' = as many as fit, 0 = pure two-pass step)")

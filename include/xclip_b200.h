@@ -47,10 +47,10 @@ long long xclip_launch_count(void);
 void xclip_launch_count_reset(void);
 /* Explicit, process-wide tuning switches for A/B measurements (never read from the environment;
  * results are identical either way).  Returns the previous value, -1 for an unknown knob.
- *   XCLIP_TUNE_FF_BWD_PREFETCH (0): xclip_ff_bwd pulls the next tile's u blocks towards L2 (default 0:
- *                                   measured 0.335 -> 0.351 ms at [50176 x 768], the kernel is not latency-bound there)
+ *   XCLIP_TUNE_FF_BWD_VARIANT (0): xclip_ff_bwd epilogue: 0 = u by ld.global -> st.shared per step,
+ *                                  1 = u by TMA one step ahead into a second box set
  *   XCLIP_TUNE_ATTN_SMALL_CTAS (1): resident CTAs per SM of the n <= 128 attention forward, 0 = built-in */
-#define XCLIP_TUNE_FF_BWD_PREFETCH 0
+#define XCLIP_TUNE_FF_BWD_VARIANT 0
 #define XCLIP_TUNE_ATTN_SMALL_CTAS 1
 #define XCLIP_TUNE_ATTN_SMALL_PREFETCH 2 /* n <= 128 attention: next item towards L2 by TMA prefetch (default 0) */
 int xclip_tune_set(int knob, int value);

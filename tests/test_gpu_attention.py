@@ -71,7 +71,7 @@ def test_attn_bwd(cuda_device, B, n, H, masked):
     for name, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
         err = (dqkv[:, sl].float() - g[:, sl]).abs().max().item()
         sc = g[:, sl].abs().max().item()
-        assert err <= 3e-2 * sc + 1e-6, f"{name}: err {err} vs scale {sc}"   # (n = 1: dq = dk = 0 exactly)
+        assert err <= 3e-2 * sc + 1e-5, f"{name}: err {err} vs scale {sc}"   # (n = 1: dq = dk = 0 up to fp32 rounding of p = 2^(s c - lse))
         rel = (dqkv[:, sl].float() - g[:, sl]).norm().item() / (g[:, sl].norm().item() + 1e-3)
         assert rel < 1e-2, f"{name}: rel fro err {rel}"
 

@@ -213,6 +213,14 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
     const bool alive = warp * 32 < p.n;
     const float c = p.scale_log2;
     uint32_t it = 0;
+    // the key-mask byte of the CTA's NEXT item is fetched while the current one is computed
+    bool keep_n = true;
+    auto fetch_mask = [&](int bh2) {
+      keep_n = true;
+      if (p.mask != nullptr && bh2 < total && (int)threadIdx.x < p.n)
+        keep_n = __ldg(p.mask + (long long)(bh2 / p.H) * p.n + threadIdx.x) != 0;
+    };
+    fetch_mask(blockIdx.x);
     for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++it) {
       const int b = bh / p.H, h = bh - b * p.H;
       const uint32_t par = it & 1;
@@ -222,11 +230,12 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnSmal
         float mul = 0.f, add = -INFINITY;
         bool masked = false;
         if (j < p.n) {
-          const bool keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
+          const bool keep = keep_n;
           mul = keep ? c : 0.f;
           add = keep ? 0.f : -FLT_MAX;
           masked = !keep;
         }
+        fetch_mask(bh + (int)gridDim.x);
         sm_sts_f(sMul + (par * ROWS + j) * 4, mul);
         sm_sts_f(sAdd + (par * ROWS + j) * 4, add);
         const uint32_t any = __ballot_sync(0xffffffffu, masked);
@@ -571,25 +580,36 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv,
     const int ce = half == 0 ? (nch + 1) / 2 : nch;
     const float c = p.scale_log2;
     uint32_t it = 0;
+    // per-row scalars (and the key-mask byte) of the CTA's NEXT item are fetched while the current one
+    // is computed: their global-load latency was the top stall of this kernel (ncu: 33 % L1TEX scoreboard)
+    float lse_n = INFINITY, delta_n = 0.f;      // +inf log-sum-exp -> p = 0 for the padding rows [n, nkp)
+    bool keep_n = false;
+    auto fetch = [&](int bh2) {
+      lse_n = INFINITY; delta_n = 0.f; keep_n = false;
+      if (bh2 < total) {
+        const int b2 = bh2 / p.H;
+        if (row < p.n) {
+          lse_n = __ldg(p.lse + (long long)bh2 * p.n + row);
+          delta_n = __ldg(p.delta + (long long)bh2 * p.n + row);
+        }
+        if (threadIdx.x < 128 && threadIdx.x < p.n)
+          keep_n = p.mask ? (__ldg(p.mask + (long long)b2 * p.n + threadIdx.x) != 0) : true;
+      }
+    };
+    fetch(blockIdx.x);
     for (int bh = blockIdx.x; bh < total; bh += gridDim.x, ++it) {
       const int b = bh / p.H, h = bh - b * p.H;
       const uint32_t par = it & 1;
+      const float lse_i = lse_n, delta_i = delta_n;
       if (threadIdx.x < 128) {
         const int j = threadIdx.x;
-        bool keep = false;
-        if (j < p.n) keep = p.mask ? (p.mask[(long long)b * p.n + j] != 0) : true;
+        const bool keep = keep_n;                // (false for j >= n)
         sm_sts_f(sMul + (par * 128 + j) * 4, keep ? c : 0.f);
         sm_sts_f(sAdd + (par * 128 + j) * 4, keep ? 0.f : -INFINITY);
         const uint32_t any = __ballot_sync(0xffffffffu, j < p.n && !keep);
         if (lane == 0) sm_sts_u32(sFlag + (par * 4 + warp) * 4, any);
       }
-      // +inf log-sum-exp -> p = 0 for the padding rows [n, nkp)
-      float lse_i = INFINITY, delta_i = 0.f;
-      if (row < p.n) {
-        const long long s_idx = ((long long)b * p.H + h) * p.n + row;
-        lse_i = __ldg(p.lse + s_idx);
-        delta_i = __ldg(p.delta + s_idx);
-      }
+      fetch(bh + (int)gridDim.x);
       const float dsc = delta_i * p.scale;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       uint32_t anym = 0;

@@ -182,6 +182,9 @@ extern "C" int xclip_ff_bwd(const void* dx, int64_t lddx, const void* w2g, const
   p.M = M; p.N = 4 * d; p.K = d; p.split_k = 1; p.alpha = 1.f;
   p.ff_stats = const_cast<float*>(stats); p.ff_ab = ab; p.ff_hidden = 4 * d;
   p.ff_u = reinterpret_cast<const bf16*>(u); p.ff_ldu = ldu;
-  p.ff_prefetch = tune(XCLIP_TUNE_FF_BWD_PREFETCH);
-  return launch_pair_ff<PEPI_FF_BWD, kMajorMN>(tmA, tmB, tmC, tmC, p, reinterpret_cast<cudaStream_t>(stream));
+  if (tune(XCLIP_TUNE_FF_BWD_VARIANT) == 0)      // older epilogue: u by ld.global -> st.shared (kept for A/B)
+    return launch_pair_ff<PEPI_FF_BWD, kMajorMN>(tmA, tmB, tmC, tmC, p, reinterpret_cast<cudaStream_t>(stream));
+  CUtensorMap tmU;                               // u = [value | gate], loaded box-wise ahead of its step
+  if ((rc = encode_2d_bf16(&tmU, u, (uint64_t)(8 * d), (uint64_t)M, (uint64_t)ldu, 64, kGemmBlockM))) return rc;
+  return launch_pair_ff<PEPI_FF_BWD2, kMajorMN>(tmA, tmB, tmC, tmU, p, reinterpret_cast<cudaStream_t>(stream));
 }

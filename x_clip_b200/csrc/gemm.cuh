@@ -68,7 +68,6 @@ struct GemmParams {
   const bf16* ff_u;        // BWD: saved [value | gate] activations [M, 8d]
   long long ff_ldu;
   const float* ff_ab;      // BWD: [M,2] per-row (mean_k(gdh), mean_k(gdh * hn)) from xclip_ff_bwd_prep
-  int ff_prefetch;         // BWD: pull the NEXT tile's u blocks towards L2 while this tile is worked on
 };
 
 constexpr int EPI_STORE = 0;    // C = alpha*acc (+bias) (+residual)

@@ -554,8 +554,23 @@ class ChunkedClipLossFn(torch.autograd.Function):
                     keep_it = k < int(retain)
                 if keep_it:
                     before = torch.cuda.memory_allocated(dev)
-                    with torch.enable_grad():
+                    z = ops = None
+                    try:
+                        with torch.enable_grad():
+                            z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                    except torch.OutOfMemoryError:
+                        # the plan was too optimistic (a fragmented cache, memory taken by someone else
+                        # since the estimate): this chunk and all later ones are re-encoded in backward
+                        z = ops = None
+                        retain = len([x for x in kept if x is not None])
+                    if z is None:
+                        torch.cuda.empty_cache()
+                        torch.cuda.set_rng_state(rng_states[-1], dev)
                         z, ops = clip._encode_to_latents(text[s:e], image[s:e], text_mask[s:e])
+                        kept.append(None)
+                        zs.append(z)
+                        opss.append(ops)
+                        continue
                     kept.append(list(z))
                     if foot is None:
                         foot = max(torch.cuda.memory_allocated(dev) - before, 1)
