@@ -591,6 +591,11 @@ def main():
                                "model": "README CLIP (cfg1/cfg2 model)", "loss_kind": LOSS_TXT[loss_k]}
             except Exception as e:
                 extras[key] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+                if os.environ.get("XCLIP_BENCH_VERBOSE"):
+                    import traceback
+                    traceback.print_exc()
+                r = None
+                torch.cuda.empty_cache()
             note(f"extra {key}: {extras[key]}")
 
     if world > 1:

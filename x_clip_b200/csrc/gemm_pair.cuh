@@ -56,11 +56,11 @@ struct PairCfg {
   static constexpr int kBox = 128 * 128;                          // one [128 rows x 64 bf16] staging box
   // STORE: 2 boxes (double buffered); FF_UP: one box per column half (value, gate and hp pass through it
   // one after the other - they wait in registers); FF_DOWN: (out, acc); FF_BWD: (d value, d gate) x 2 halves
-  // FF_BWD2: two SETS of (value, gate) boxes per column half - while one set is worked on / stored, the
-  // other receives the next step's u by TMA - paid for with two mainloop stages (the dgrad GEMM has
-  // K = d <= 1024 and runs far below the tensor peak here: the kernel is bound by its epilogue)
-  static constexpr int kStagingBytes = (EPI == PEPI_FF_BWD2 ? 8 : EPI == PEPI_FF_BWD ? 4 : 2) * kBox;
-  static constexpr int kStages = EPI == PEPI_FF_BWD2 ? 3 : EPI == PEPI_FF_BWD ? 5 : 6;
+  // FF_BWD2: three SETS of (value, gate) boxes rotate through "being loaded by TMA / worked on / being
+  // stored" - paid for with one mainloop stage (with three stages the epilogue waited for the MMAs,
+  // with four it does not: the dgrad GEMM has K = d <= 1024 and the kernel is bound by its epilogue)
+  static constexpr int kStagingBytes = (EPI == PEPI_FF_BWD2 ? 6 : EPI == PEPI_FF_BWD ? 4 : 2) * kBox;
+  static constexpr int kStages = EPI == PEPI_FF_BWD2 ? 4 : EPI == PEPI_FF_BWD ? 5 : 6;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kScratchBytes = EPI == PEPI_FF_UP ? 2 * 128 * 8 : 0;   // row-sum exchange
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + kScratchBytes;
@@ -125,7 +125,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_empty[i], 2 * kEpiWarps);
     }
     if (EPI == PEPI_FF_BWD2)
-      for (int i = 0; i < 4; ++i) mbar_init(&bars[16 + i], 1);     // u_full[column half][set]
+      for (int i = 0; i < 3; ++i) mbar_init(&bars[16 + i], 1);     // u_full[set]
     fence_barrier_init();
   }
   if (warp == kEpiWarps && XCLIP_ONE_LANE(lane)) {
@@ -225,16 +225,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = quarter * 32 + lane;
     // ---- FF_BWD2 state: u_full barriers, the TMA load of one step's (value, gate) boxes, row scalars
     uint64_t* u_full = bars + 16;
-    auto load_u = [&](int tile, int q, int bhalf_) {
-      const int tmn_ = tile % (num_n * num_m2);
-      const int kq_ = (tmn_ % num_n) * BLOCK_N + bhalf_ * 128 + q * 64;
+    // step g of this CTA = 64-column group q = g & 3 of its (g >> 2)-th tile; box set g % 3
+    auto load_u = [&](int g) {
+      const int tmn_ = (pair + (g >> 2) * npairs) % (num_n * num_m2);
+      const int kq_ = (tmn_ % num_n) * BLOCK_N + (g & 3) * 64;
       const int r0_ = ((tmn_ / num_n) * 2 + (int)rank) * kGemmBlockM;
-      uint8_t* dst = smem_c + (bhalf_ * 2 + q) * 2 * S::kBox;
-      uint64_t* bar = &u_full[bhalf_ * 2 + q];
+      uint8_t* dst = smem_c + (g % 3) * 2 * S::kBox;
+      uint64_t* bar = &u_full[g % 3];
       mbar_arrive_expect_tx(bar, 2 * S::kBox);
       tma_load_2d(dst, &tmC2, bar, kq_, r0_);                         // u[:, k ..]        value
       tma_load_2d(dst + S::kBox, &tmC2, bar, p.ff_hidden + kq_, r0_);  // u[:, 4d + k ..]   gate
     };
+    const int my_steps = pair < num_tiles ? 4 * ((num_tiles - pair + npairs - 1) / npairs) : 0;
     float2 nst = make_float2(0.f, 0.f), nab = make_float2(0.f, 0.f);   // (mean, rstd), (a, b) of the NEXT tile's row
     auto load_row_scalars = [&](int tile) {
       nst = make_float2(0.f, 0.f); nab = make_float2(0.f, 0.f);
@@ -248,10 +250,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     if constexpr (EPI == PEPI_FF_BWD2) {
-      const int bhalf_ = warp >> 3;
-      if (threadIdx.x == bhalf_ * 256 && pair < num_tiles) {       // steps 0 and 1: both column groups of the first tile
-        load_u(pair, 0, bhalf_);
-        load_u(pair, 1, bhalf_);
+      if (threadIdx.x == 0 && my_steps > 0) {       // steps 0 and 1 (a CTA with a tile has four steps)
+        load_u(0);
+        load_u(1);
       }
       load_row_scalars(pair);
     }
@@ -447,70 +448,65 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else if constexpr (EPI == PEPI_FF_BWD2) {
         // Same arithmetic as PEPI_FF_BWD, different data movement.  The older epilogue fetched u with
         // ld.global -> st.shared at the start of every 64-column step and its warps then sat on the HBM
-        // latency (ncu: 26 % long-scoreboard at the STS + 22 % barrier stalls behind it).  Here a step's
-        // (value, gate) boxes arrive by TMA in the box SET the previous-but-one step used, requested half
-        // a step earlier by the column half's issuer thread once that set's gradient store has been read:
-        //   step g = 2 it + q uses set q;  L(g) = TMA load of step g;  S(g) = TMA store of step g
-        //   prologue: L(0), L(1);   middle of step g >= 1: wait S(<= g-1) read, issue L(g+1)
+        // latency (ncu: 26 % long-scoreboard at the STS + 22 % barrier stalls behind it).  Here all 16
+        // warps work on one 64-column step at a time (a warp: its 32-row lane quarter x 16 columns) and a
+        // step's (value, gate) boxes arrive by TMA in one of THREE box sets, requested one and a half steps
+        // ahead by thread 0 as soon as the set's previous gradient store has been read:
+        //   step g uses set g % 3;   L(g) = TMA load of step g;   S(g) = TMA store of step g
+        //   prologue: L(0), L(1);    middle of step g: wait S(<= g-1) read, issue L(g+2)
         // The gradients overwrite u in place and leave by TMA store as before.
-        const int sub = warp >> 2;
-        const int bhalf = sub >> 1;
-        const int part = sub & 1;                                      // which 32 columns of a group
-        const bool issuer = (threadIdx.x == bhalf * 256);
+        const int cs = warp >> 2;                                      // which 16 columns of the 64-column step
+        const bool issuer = threadIdx.x == 0;
         const float mean = nst.x, rstd = nst.y, am = nab.x, bm = nab.y;
         load_row_scalars(t + npairs);                                  // next tile's scalars travel during this one
         const f32x2 rstd2 = f2_splat(rstd), nmr = f2_splat(-mean * rstd), namr = f2_splat(-am * rstd),
                     nbmr = f2_splat(-bm * rstd);
 #pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          const int kq = n_blk * BLOCK_N + bhalf * 128 + q * 64;
-          const uint32_t stg = smem_u32(smem_c) + (bhalf * 2 + q) * 2 * S::kBox;   // value -> d value | gate -> d gate
-          mbar_wait(&u_full[bhalf * 2 + q], it & 1);
+        for (int q = 0; q < 4; ++q) {
+          const int g = 4 * it + q;
+          const int set = g % 3;
+          const int kq = n_blk * BLOCK_N + q * 64;
+          const uint32_t stg = smem_u32(smem_c) + set * 2 * S::kBox;   // value -> d value | gate -> d gate
+          mbar_wait(&u_full[set], (g / 3) & 1);
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + q * 64 + cs * 16, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c16 = 0; c16 < 2; ++c16) {
-            if (c16 == 1 && issuer && (it > 0 || q > 0)) {
-              // the other set: its last store was committed a step ago - by now it has long been read
-              const int tile2 = (q == 0) ? t : t + npairs;
-              if (tile2 < num_tiles) {
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                load_u(tile2, q ^ 1, bhalf);
-              }
+          for (int i = 0; i < 16; i += 8) {
+            if (i == 8 && issuer && g + 2 < my_steps) {
+              // set (g+2) % 3 = (g-1) % 3: its store was committed half a step ago and has been read by now
+              if (g >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              load_u(g + 2);
             }
-            uint32_t v[16];
-            tmem_ld_32x16(taddr + bhalf * 128 + q * 64 + part * 32 + c16 * 16, v);
-            tmem_ld_wait();
+            const int chunk = cs * 2 + (i >> 3);
+            const uint32_t off = swz128(row_in_tile, chunk);
+            uint32_t wv[4], wg[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(stg + off));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(wg[0]), "=r"(wg[1]), "=r"(wg[2]), "=r"(wg[3]) : "r"(stg + S::kBox + off));
+            uint32_t dvw[4], dgw[4];
 #pragma unroll
-            for (int i = 0; i < 16; i += 8) {
-              const int chunk = part * 4 + c16 * 2 + (i >> 3);
-              const uint32_t off = swz128(row_in_tile, chunk);
-              uint32_t wv[4], wg[4];
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(stg + off));
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(wg[0]), "=r"(wg[1]), "=r"(wg[2]), "=r"(wg[3]) : "r"(stg + S::kBox + off));
-              uint32_t dvw[4], dgw[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {                           // two columns per step (fp32x2)
-                const float g0 = __uint_as_float(wg[k] << 16), g1 = __uint_as_float(wg[k] & 0xffff0000u);
-                const f32x2 gate = f2_pack(g0, g1), val = f2_from_bf16x2(wv[k]);
-                const GeluParts2 gp = gelu_parts2(g0, g1);
-                const f32x2 ge = f2_mul(gate, gp.cdf);                // gelu(gate)
-                const f32x2 gd = f2_fma(gate, gp.pdf, gp.cdf);        // gelu'(gate)
-                const f32x2 hn = f2_fma(f2_mul(val, ge), rstd2, nmr); // (val*ge - mean) rstd
-                f32x2 dhp = f2_fma(f2_pack(__uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1])),
-                                   rstd2, namr);                      // rstd (gdh - a)
-                dhp = f2_fma(hn, nbmr, dhp);                          //   - rstd b hn
-                dvw[k] = f2_to_bf16x2(f2_mul(dhp, ge));
-                dgw[k] = f2_to_bf16x2(f2_mul(f2_mul(dhp, val), gd));
-              }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(dvw[0]),
-                           "r"(dvw[1]), "r"(dvw[2]), "r"(dvw[3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(dgw[0]),
-                           "r"(dgw[1]), "r"(dgw[2]), "r"(dgw[3]) : "memory");
+            for (int k = 0; k < 4; ++k) {                           // two columns per step (fp32x2)
+              const float g0 = __uint_as_float(wg[k] << 16), g1 = __uint_as_float(wg[k] & 0xffff0000u);
+              const f32x2 gate = f2_pack(g0, g1), val = f2_from_bf16x2(wv[k]);
+              const GeluParts2 gp = gelu_parts2(g0, g1);
+              const f32x2 ge = f2_mul(gate, gp.cdf);                // gelu(gate)
+              const f32x2 gd = f2_fma(gate, gp.pdf, gp.cdf);        // gelu'(gate)
+              const f32x2 hn = f2_fma(f2_mul(val, ge), rstd2, nmr); // (val*ge - mean) rstd
+              f32x2 dhp = f2_fma(f2_pack(__uint_as_float(v[i + 2 * k]), __uint_as_float(v[i + 2 * k + 1])),
+                                 rstd2, namr);                      // rstd (gdh - a)
+              dhp = f2_fma(hn, nbmr, dhp);                          //   - rstd b hn
+              dvw[k] = f2_to_bf16x2(f2_mul(dhp, ge));
+              dgw[k] = f2_to_bf16x2(f2_mul(f2_mul(dhp, val), gd));
             }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(dvw[0]),
+                         "r"(dvw[1]), "r"(dvw[2]), "r"(dvw[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + S::kBox + off), "r"(dgw[0]),
+                         "r"(dgw[1]), "r"(dgw[2]), "r"(dgw[3]) : "memory");
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 256;" ::"r"(1 + bhalf) : "memory");
+          asm volatile("bar.sync 1, 512;" ::: "memory");
           if (issuer) {
             const int r0 = m_blk * kGemmBlockM;
             tma_store_2d(&tmC, stg, kq, r0);                            // du[:, k ..]        d value

@@ -188,19 +188,24 @@ class TransformerFn(torch.autograd.Function):
                 w1p, w2g, colvec = ff_weights(w1, w2, g4)
                 u, h, rowsum = K.ff_up(xn2, w1p, need_u=need_bwd)
                 x2, acc, st_v = K.ff_down(h, w2g, colvec, rowsum, x1, LN_EPS)
-                ff_saved.append((w2g, colvec, acc))
+                if need_bwd:
+                    ff_saved.append((w2g, colvec, acc))
             else:
                 u = K.gemm(xn2, b1)
                 h, st_v = K.geglu_ln_fwd(u, g4, eps=LN_EPS)
                 x2 = K.gemm(h, b2, residual=x1)
-            saved.append((xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h))
+            # forward-only sweeps keep NOTHING alive beyond the layer (the list below would otherwise hold
+            # every layer's activations until the call returns: ~14 of the 22 d per token-layer)
+            if need_bwd:
+                saved.append((xcur, st1, xn, qkv, o, lse, y, st_y, x1, st_x1, xn2, u, st_v, h))
+            del qkv, o, lse, y, x1, xn2, u, h
             xcur = x2
             if L + 1 < depth:
                 xn, st1, _, _ = K.layernorm_fwd(xcur, layers[L + 1][0], eps=LN_EPS)
         out, st_out, _, _ = K.layernorm_fwd(xcur, g_out, eps=LN_EPS)
 
         ctx.saved = saved
-        ctx.tail = (x_in, st_in, xcur, st_out)
+        ctx.tail = (x_in, st_in, xcur, st_out) if need_bwd else None
         ctx.mask = mask_c
         ctx.dims = (B, n, d, heads, depth, scale, causal)
         ctx.rot = (rot_cos, rot_sin)
