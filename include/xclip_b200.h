@@ -48,7 +48,8 @@ void xclip_launch_count_reset(void);
 /* Explicit, process-wide tuning switches for A/B measurements (never read from the environment;
  * results are identical either way).  Returns the previous value, -1 for an unknown knob.
  *   XCLIP_TUNE_FF_BWD_VARIANT (0): xclip_ff_bwd epilogue: 0 = u by ld.global -> st.shared per step,
- *                                  1 = u by TMA one step ahead into a second box set
+ *                                  1 (default) = u by TMA one and a half steps ahead into one of three
+ *                                  rotating box sets (0.346 -> 0.297 ms at [50176 x 768], bit-identical)
  *   XCLIP_TUNE_ATTN_SMALL_CTAS (1): resident CTAs per SM of the n <= 128 attention forward, 0 = built-in */
 #define XCLIP_TUNE_FF_BWD_VARIANT 0
 #define XCLIP_TUNE_ATTN_SMALL_CTAS 1

@@ -243,7 +243,7 @@ def test_microbatched_step_equals_single_pass(cuda_device):
     clip.load_state_dict(state)
     clip.train()
     out = []
-    for keep in (0, 0, 1, "auto"):
+    for keep in (0, 0, 1, "auto", "auto"):      # (the second "auto" step repeats the remembered plan)
         clip.microbatch_retain = keep
         torch.manual_seed(7)
         for p in clip.parameters():

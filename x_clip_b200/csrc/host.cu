@@ -136,7 +136,7 @@ int encode_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t m
 }  // namespace xclip
 
 namespace xclip {
-static int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static int g_tune[8] = {1, 0, 0, 0, 0, 0, 0, 0};   // XCLIP_TUNE_FF_BWD_VARIANT = 1 (TMA-pipelined)
 int tune(int knob) { return (knob >= 0 && knob < 8) ? g_tune[knob] : 0; }
 }  // namespace xclip
 

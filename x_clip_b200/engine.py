@@ -545,10 +545,22 @@ class ChunkedClipLossFn(torch.autograd.Function):
         bounds = [(s, min(s + chunk, B)) for s in range(0, B, chunk)]
         rng_states, zs, opss, kept = [], [], [], []
         foot = None                                   # bytes of one retained chunk's activations
+        # "auto" plans ONCE per (batch, chunk size): the first step measures and decides, later steps
+        # repeat its decision - the same tensors are then allocated in the same order every step, which
+        # is what keeps torch's caching allocator free of fragmentation this close to the HBM limit
+        plans = clip.__dict__.setdefault("_retain_plans", {})
+        plan_key = (B, chunk, str(dev))
+        planned = retain == "auto" and plan_key not in plans
+        keep_mask = None                              # a remembered plan: which chunks stay resident
+        if retain == "auto" and not planned:
+            keep_mask = plans[plan_key]
+        oom_fallbacks = 0
         with torch.no_grad(), weight_scope():
             for k, (s, e) in enumerate(bounds):
                 rng_states.append(torch.cuda.get_rng_state(dev))
-                if retain == "auto":
+                if keep_mask is not None:
+                    keep_it = keep_mask[k]
+                elif retain == "auto":
                     scale = (e - s) / float(chunk)
                     if foot is None:                  # first chunk: keep it, measure it
                         keep_it = True
@@ -567,7 +579,8 @@ class ChunkedClipLossFn(torch.autograd.Function):
                         # the plan was too optimistic (a fragmented cache, memory taken by someone else
                         # since the estimate): this chunk and all later ones are re-encoded in backward
                         z = ops = None
-                        retain = len([x for x in kept if x is not None])
+                        retain, keep_mask = 0, None   # (an int plan: nothing further is kept)
+                        oom_fallbacks += 1
                     if z is None:
                         torch.cuda.empty_cache()
                         torch.cuda.set_rng_state(rng_states[-1], dev)
@@ -579,7 +592,7 @@ class ChunkedClipLossFn(torch.autograd.Function):
                     kept.append(list(z))
                     if foot is None:
                         foot = max(torch.cuda.memory_allocated(dev) - before, 1)
-                        if retain == "auto" and len(bounds) > 1 and \
+                        if planned and len(bounds) > 1 and \
                                 _avail_bytes(dev) < foot * (1.0 + RETAIN_TRANSIENT_FRAC) + RETAIN_MARGIN_BYTES:
                             kept[-1] = None           # not even a second live chunk fits beside it: let it go
                     z = [t.detach() for t in z]
@@ -601,8 +614,11 @@ class ChunkedClipLossFn(torch.autograd.Function):
         ctx.clip, ctx.inputs = clip, (text, image, text_mask)
         ctx.bounds, ctx.rng_states, ctx.kept = bounds, rng_states, kept
         ctx.graph = (loss, leaves, temp_leaf)
-        clip.last_step_plan = dict(chunks=len(bounds), retained=sum(z is not None for z in kept),
-                                   chunk_activation_bytes=foot)
+        n_kept = sum(z is not None for z in kept)
+        if planned or (oom_fallbacks and plan_key in plans):
+            plans[plan_key] = [z is not None for z in kept]    # WHICH chunks stay resident
+        clip.last_step_plan = dict(chunks=len(bounds), retained=n_kept, chunk_activation_bytes=foot,
+                                   oom_fallbacks=oom_fallbacks)
         return loss.detach()
 
     @staticmethod
