@@ -56,6 +56,8 @@ for (M, d) in shapes:
     t["gemm dgrad down (plain)"] = timeit(lambda: K.gemm(dx, w2b, b_major=1))
     t["geglu_ln_bwd"] = timeit(lambda: K.geglu_ln_bwd(dh, u, st, g4))
     t["ff_bwd_prep"] = timeit(lambda: K.ff_bwd_prep(dx, stats))
+    t["gemm wgrad up (plain, split-K fp32)"] = timeit(lambda: K.gemm(u, x, a_major=1, b_major=1, accumulate=True))
+    t["gemm dgrad up (plain)"] = timeit(lambda: K.gemm(u, w1b, b_major=1))
     if hasattr(K, "ff_bwd"):
         dxs, vsum, ab = K.ff_bwd_prep(dx, stats, acc, colvec)
         t["ff_bwd (fused dgrad + LN/GEGLU bwd)"] = timeit(lambda: K.ff_bwd(dx, w2g, u, stats, ab))

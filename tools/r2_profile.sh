@@ -13,4 +13,6 @@ tools/ncu_kernel.sh nce_bwd gemm_bf16_kernelILi256ELi0ELi0ELi2E 1 1 python tools
 tools/ncu_kernel.sh pair_store gemm_pair_kernelILi0ELi0ELi0E 3 1 python tools/ff_bench.py 50176,768
 tools/ncu_kernel.sh ff_up gemm_pair_kernelILi0ELi0ELi1E 2 1 python tools/ff_bench.py 50176,768
 tools/ncu_kernel.sh ff_down gemm_pair_kernelILi0ELi0ELi2E 2 1 python tools/ff_bench.py 50176,768
-tools/ncu_kernel.sh ff_bwd gemm_pair_kernelILi0ELi1ELi3E 2 1 python tools/ff_bench.py 50176,768
+tools/ncu_kernel.sh ff_bwd gemm_pair_kernelILi0ELi1ELi4E 2 1 python tools/ff_bench.py 50176,768
+tools/ncu_kernel.sh pair_wgrad gemm_pair_kernelILi1ELi1ELi0E 2 1 python tools/ff_bench.py 50176,768
+tools/ncu_kernel.sh pair_dgrad gemm_pair_kernelILi0ELi1ELi0E 2 1 python tools/ff_bench.py 50176,768
