@@ -27,7 +27,7 @@ ALG = {
     "ff_down": ("fused FF-down: GEMM + LayerNorm fold + residual", 2.0 * M * 4 * d * d, 2.0 * (M * 4 * d + 4 * d * d + 3 * M * d)),
     "ff_bwd": ("fused FF backward: dgrad GEMM + LayerNorm/GEGLU backward epilogue (TMA-pipelined u, variant 1)", 2.0 * M * 4 * d * d, 2.0 * (M * d + 4 * d * d + 16 * M * d)),
     "pair_wgrad": (f"CTA-pair wgrad [{8 * d}x{M}]x[{M}x{d}] (FF-up weight gradient, split-K, fp32 red.add)", 2.0 * M * 8 * d * d, 2.0 * (M * 8 * d + M * d) + 4.0 * 8 * d * d),
-    "pair_dgrad": (f"CTA-pair dgrad [{M}x{8 * d}]x[{8 * d}x{d}] (FF-up input gradient)", 2.0 * M * 8 * d * d, 2.0 * (M * 8 * d + 8 * d * d + M * d)),
+    "pair_dgrad": (f"CTA-pair dgrad [{M}x{d}]x[{d}x{4 * d}] (MN-major B operand; the un-fused FF-down input gradient)", 2.0 * M * 4 * d * d, 2.0 * (M * d + 4 * d * d + M * 4 * d)),
 }
 
 
