@@ -256,6 +256,55 @@ def test_microbatched_step_equals_single_pass(cuda_device):
         assert (out[0][1] - o[1]).abs().max().item() <= 1e-3 * out[0][1].abs().max().item()
 
 
+def test_microbatched_step_survives_an_out_of_memory_retained_chunk(cuda_device):
+    """If keeping a chunk's activations runs out of memory (a fragmented allocator cache, memory taken by
+    someone else since the plan was made) the step must fall back to re-encoding that chunk and the later
+    ones - same loss, same gradients, same PatchDropout draw - and remember the smaller plan."""
+    from oracle import clip_oracle as O
+    import x_clip_b200
+    gold = json.loads((GOLD / "tiny_dcl_extra.json").read_text())
+    cfg = O.ClipConfig(**gold["cfg"])
+    state = O.protocol_state_dict(cfg, 1234)
+    text, image = O.protocol_inputs(cfg, 6, 4321, 0.2)
+    text, image = text.to(cuda_device), image.to(cuda_device)
+    clip = x_clip_b200.CLIP(**gold["cfg"], visual_patch_dropout=0.5, microbatch=2).to(cuda_device)
+    clip.load_state_dict(state)
+    clip.train()
+
+    def step():
+        torch.manual_seed(11)
+        for p in clip.parameters():
+            p.grad = None
+        loss = clip(text, image, return_loss=True)
+        loss.backward()
+        return loss.item(), clip.to_visual_latent.weight.grad.clone(), clip.text_transformer.token_emb.weight.grad.clone()
+
+    ref = step()                                       # all three chunks resident
+    assert clip.last_step_plan["retained"] == 3 and clip.last_step_plan["oom_fallbacks"] == 0
+    real = clip._encode_to_latents
+    calls = {"n": 0}
+
+    def flaky(*a, **k):
+        calls["n"] += 1
+        if calls["n"] == 2 and torch.is_grad_enabled():   # the second chunk's retained encode "runs out of memory"
+            raise torch.OutOfMemoryError("injected by the test")
+        return real(*a, **k)
+
+    clip._encode_to_latents = flaky
+    try:
+        got = step()
+    finally:
+        clip._encode_to_latents = real
+    plan = clip.last_step_plan
+    assert plan["oom_fallbacks"] == 1 and plan["retained"] == 1, plan
+    assert got[0] == ref[0]
+    for a, b in zip(got[1:], ref[1:]):
+        assert (a - b).abs().max().item() <= 1e-3 * b.abs().max().item() + 1e-7
+    again = step()                                     # the smaller plan is remembered
+    assert clip.last_step_plan["retained"] == 1 and clip.last_step_plan["oom_fallbacks"] == 0
+    assert again[0] == ref[0]
+
+
 def test_pluggable_encoders_freeze_and_maskless(cuda_device):
     """Hooks of the reference surface (x_clip.py:482-483, 501-502, 604-605, 659-660): foreign
     encoders returning [B,n,d] / [B,d], freeze_* flags, text_encode_without_mask."""
