@@ -54,6 +54,8 @@ void xclip_launch_count_reset(void);
 #define XCLIP_TUNE_FF_BWD_VARIANT 0
 #define XCLIP_TUNE_ATTN_SMALL_CTAS 1
 #define XCLIP_TUNE_ATTN_SMALL_PREFETCH 2 /* n <= 128 attention: next item towards L2 by TMA prefetch (default 0) */
+#define XCLIP_TUNE_LN_FWD_BLOCKS 3 /* LayerNorm forward: cap on resident blocks per SM (0 = built-in 8) */
+#define XCLIP_TUNE_LN_BWD_BLOCKS 4 /* LayerNorm backward: blocks per SM (0 = built-in 2) */
 int xclip_tune_set(int knob, int value);
 
 /* ---- dense contraction (tcgen05) --------------------------------------

@@ -662,7 +662,10 @@ extern "C" int xclip_layernorm_fwd(const void* x, int64_t ldx, const float* g, c
                     (!g2 || (ALIGNED16(g2) && out2 && ALIGNED16(out2))),
                 "layernorm_fwd: pointers must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_NARROW(ln_fwd_kernel, d, row_grid(rows), s, (const bf16*)x, ldx, g, (const bf16*)res,
+  int fgrid = row_grid(rows);
+  if (tune(XCLIP_TUNE_LN_FWD_BLOCKS) > 0 && fgrid > num_sms() * tune(XCLIP_TUNE_LN_FWD_BLOCKS))
+    fgrid = num_sms() * tune(XCLIP_TUNE_LN_FWD_BLOCKS);
+  DISPATCH_NARROW(ln_fwd_kernel, d, fgrid, s, (const bf16*)x, ldx, g, (const bf16*)res,
                   ldres, (bf16*)out, ldo, stats, g2, (bf16*)out2, ldo2, stats2, rows, eps)
   XCLIP_LAUNCH_CHECK("ln_fwd_kernel");
   return XCLIP_OK;
@@ -682,7 +685,8 @@ extern "C" int xclip_layernorm_bwd(const void* dy, int64_t lddy, const void* x, 
                     (!add || ALIGNED16(add)),
                 "layernorm_bwd: pointers must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = row_grid(rows) < num_sms() * 2 ? row_grid(rows) : num_sms() * 2;
+  const int per_sm = tune(XCLIP_TUNE_LN_BWD_BLOCKS) > 0 ? tune(XCLIP_TUNE_LN_BWD_BLOCKS) : 2;
+  const int grid = row_grid(rows) < num_sms() * per_sm ? row_grid(rows) : num_sms() * per_sm;
   DISPATCH_NARROW(ln_bwd_kernel, d, grid, s, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, g,
                   (const bf16*)add, ldadd, (bf16*)dx, lddx, dg, rows)
   XCLIP_LAUNCH_CHECK("ln_bwd_kernel");

@@ -64,13 +64,21 @@ def weight_bf16(p: torch.Tensor) -> torch.Tensor:
 
 
 class weight_scope:
-    """Share bf16 weight casts between the encoder calls of ONE sweep over micro-batches."""
+    """Share bf16 weight casts between the encoder calls of ONE sweep over micro-batches.
+    `cache`: continue with the casts of an earlier scope (the backward sweep of a step reuses the
+    forward sweep's - autograd semantics: backward sees the weights of its forward)."""
+
+    def __init__(self, cache=None):
+        self.given = cache
 
     def __enter__(self):
         global _scope_cache
         self.prev = _scope_cache
-        if _scope_cache is None:
+        if self.given is not None:
+            _scope_cache = self.given
+        elif _scope_cache is None:
             _scope_cache = {}
+        self.cache = _scope_cache
         return self
 
     def __exit__(self, *exc):
@@ -555,7 +563,7 @@ class ChunkedClipLossFn(torch.autograd.Function):
         if retain == "auto" and not planned:
             keep_mask = plans[plan_key]
         oom_fallbacks = 0
-        with torch.no_grad(), weight_scope():
+        with torch.no_grad(), weight_scope() as wscope:
             for k, (s, e) in enumerate(bounds):
                 rng_states.append(torch.cuda.get_rng_state(dev))
                 if keep_mask is not None:
@@ -614,6 +622,7 @@ class ChunkedClipLossFn(torch.autograd.Function):
         ctx.clip, ctx.inputs = clip, (text, image, text_mask)
         ctx.bounds, ctx.rng_states, ctx.kept = bounds, rng_states, kept
         ctx.graph = (loss, leaves, temp_leaf)
+        ctx.weight_casts = wscope.cache
         n_kept = sum(z is not None for z in kept)
         if planned or (oom_fallbacks and plan_key in plans):
             plans[plan_key] = [z is not None for z in kept]    # WHICH chunks stay resident
@@ -635,7 +644,7 @@ class ChunkedClipLossFn(torch.autograd.Function):
         # retained chunks first: their backward releases HBM before any chunk is re-encoded
         order = [k for k in range(len(ctx.bounds)) if kept[k] is not None] + \
                 [k for k in range(len(ctx.bounds)) if kept[k] is None]
-        with weight_scope():
+        with weight_scope(ctx.weight_casts):
             for pos, k in enumerate(order):
                 s, e = ctx.bounds[k]
                 # parameter gradients accumulate over the chunks; gradient-sync hooks (GradSync)
@@ -651,5 +660,5 @@ class ChunkedClipLossFn(torch.autograd.Function):
                     torch.autograd.backward(list(z), [d[s:e] for d in dz])   # accumulates into .grad
                     del z
         torch.cuda.set_rng_state(keep_state, dev)
-        ctx.graph = ctx.inputs = ctx.kept = None
+        ctx.graph = ctx.inputs = ctx.kept = ctx.weight_casts = None
         return None, None, None, None, None, temp_leaf.grad, None
