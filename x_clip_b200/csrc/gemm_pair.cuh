@@ -54,14 +54,16 @@ struct PairCfg {
   static constexpr int kBBytes = 128 * kGemmBlockK * 2;           // 16 KiB: this CTA's 128 of 256 N columns
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBox = 128 * 128;                          // one [128 rows x 64 bf16] staging box
-  // STORE: 2 boxes (double buffered); FF_UP: two boxes per column half (value, gate, hp rotate through
-  // them: a box is rewritten two stores after it was handed to TMA, so its read has long finished);
-  // FF_DOWN: two (out, acc) box pairs alternating by 64-column step; FF_BWD: (d value, d gate) x 2 halves
+  // STORE: 2 boxes (double buffered); FF_UP: one box per column half (value, gate and hp pass through it
+  // one after the other - they wait in registers; a second box per half was measured: it removes the
+  // barrier stalls but costs the sixth mainloop stage, 0.366 -> 0.384 ms at K = 768); FF_DOWN: two
+  // (out, acc) box pairs alternating by 64-column step; FF_BWD: (d value, d gate) x 2 halves
   // FF_BWD2: three SETS of (value, gate) boxes rotate through "being loaded by TMA / worked on / being
   // stored" - paid for with one mainloop stage (with three stages the epilogue waited for the MMAs,
   // with four it does not: the dgrad GEMM has K = d <= 1024 and the kernel is bound by its epilogue)
-  static constexpr int kStagingBytes = (EPI == PEPI_FF_BWD2 ? 6 : EPI == PEPI_STORE ? 2 : 4) * kBox;
-  static constexpr int kStages = EPI == PEPI_FF_BWD2 ? 4 : EPI == PEPI_STORE ? 6 : 5;
+  static constexpr int kStagingBytes =
+      (EPI == PEPI_FF_BWD2 ? 6 : (EPI == PEPI_STORE || EPI == PEPI_FF_UP) ? 2 : 4) * kBox;
+  static constexpr int kStages = EPI == PEPI_FF_BWD2 ? 4 : (EPI == PEPI_STORE || EPI == PEPI_FF_UP) ? 6 : 5;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kScratchBytes = EPI == PEPI_FF_UP ? 2 * 128 * 8 : 0;   // row-sum exchange
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarrierBytes + kScratchBytes;
@@ -277,7 +279,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // of (value, gate, hp) boxes [128 rows x 64 columns].
         const int sub = warp >> 2;
         const int bs = sub >> 1;                                      // box set
-        const uint32_t stg0 = smem_u32(smem_c) + bs * 2 * S::kBox;    // this column half's two staging boxes
+        const uint32_t stg = smem_u32(smem_c) + bs * S::kBox;         // this column half's staging box
         const bool issuer = (threadIdx.x == bs * 256);
         // All arithmetic happens BEFORE the staging boxes are touched: the results wait in registers
         // (48 packed words) while the previous tile's TMA stores are still draining the boxes, so the
@@ -320,20 +322,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // row, box set and tile instead of two)
         float2* xch = reinterpret_cast<float2*>(smem_c + S::kStagingBytes + S::kBarrierBytes) + bs * 128;
         if (sub & 1) xch[row_in_tile] = make_float2(s1, s2);
-        // value -> box 0, gate -> box 1, hp -> box 0 again.  A box is only rewritten after the store that
-        // last read it has finished reading: before `value` that store is a whole tile old, before `hp` it
-        // is the value store issued two passes ago (one younger store - gate - may still be pending).
-        // (With a single box every pass waited for the store issued a moment earlier: ncu showed 38 % of
-        // the warp samples at these barriers.)
+        // value, gate and hp pass through the single box one after the other
         const int hcol = n_blk * 128 + bs * 64;               // hidden-unit column of this box
         const int r0 = m_blk * kGemmBlockM;
 #pragma unroll
         for (int which = p.ff_skip_u ? 2 : 0; which < 3; ++which) {
-          const uint32_t stg = stg0 + (which == 1 ? S::kBox : 0);
-          if (issuer) {
-            if (which == 2 && !p.ff_skip_u) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else if (which != 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 256;" ::"r"(1 + bs) : "memory");
           const uint32_t* src = which == 0 ? pv : (which == 1 ? pg : ph);
 #pragma unroll
