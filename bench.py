@@ -665,7 +665,7 @@ def main():
                       "u (8d, skipped in forward-only sweeps) + hp (4d)"),
             "down": sub(["ff_down"], "gemm_pair_kernel<PEPI_FF_DOWN> (down-projection GEMM + LayerNorm fold + residual)",
                         "flops = the GEMM only (2*M*4d*d)"),
-            "bwd": sub(["ff_bwd"], "gemm_pair_kernel<PEPI_FF_BWD> (dgrad GEMM + LayerNorm/GEGLU backward epilogue)",
+            "bwd": sub(["ff_bwd"], "gemm_pair_kernel<PEPI_FF_BWD2> (dgrad GEMM + LayerNorm/GEGLU backward epilogue, u by TMA one and a half steps ahead)",
                        "flops = the GEMM only (2*M*4d*d); reads u 8d, writes du 8d: HBM-bound by design")}
         roofline["attention"] = {
             "fwd": sub(["attn_fwd"], "attn_fwd_small_kernel / attn_fwd_wg_kernel",
