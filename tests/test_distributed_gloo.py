@@ -181,6 +181,36 @@ def _gs_worker(rank, world, port, q):
         for w, p in zip(want, ref_net.parameters()):
             w += p.grad / world
     errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
+    # the same step with in-place gradient accumulation (engine._accumulate_into_grad): the middle
+    # chunk adds its parameter gradients straight into `.grad` and hands autograd nothing, the hooks
+    # fire only in the last chunk - and must then see (and reduce) the sum over ALL chunks
+    class ChunkedInPlace(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            ctx.x = x
+            with torch.no_grad():
+                return sum(net(c).square().sum() for c in x.chunk(3))
+
+        @staticmethod
+        def backward(ctx, g):
+            chunks = ctx.x.chunk(3)
+            params = [p for p in net.parameters()]
+            for k, c in enumerate(chunks):
+                with torch.enable_grad(), D.defer_grad_sync(k != len(chunks) - 1):
+                    loss = net(c).square().sum()
+                    if k == 1:                                # "kernels accumulate into .grad, return None"
+                        gs = torch.autograd.grad(loss, params, g)
+                        for p_, g_ in zip(params, gs):
+                            p_.grad.add_(g_)
+                    else:
+                        torch.autograd.backward(loss, g)
+            return None
+
+    mod.zero_grad(set_to_none=True)
+    ChunkedInPlace.apply(dch[rank].requires_grad_(True)).backward()
+    sync.finish()
+    got = [p.grad.clone() for p in net.parameters()]
+    errs.append(max((g - w).abs().max().item() for g, w in zip(got, want)))
     # without the deferral the second arrival of a parameter is an error, not a silent wrong result
     mod.zero_grad(set_to_none=True)
     raised = False
