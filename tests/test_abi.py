@@ -53,3 +53,24 @@ def test_product_never_imports_oracle():
     for f in (ROOT / "x_clip_b200").rglob("*.py"):
         assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle", f.read_text(), re.M), f
         assert "oracle" not in f.read_text(), f   # not even mentioned: keeps the boundary obvious
+
+
+def test_library_sass_is_tcgen05_tma_code():
+    """The shipped kernels are sm_100a tcgen05 / TMEM / TMA code, not recompiled mma.sync / cp.async:
+    the SASS of libxclip_b200.so must contain the Blackwell tensor-core, tensor-memory and bulk-tensor
+    opcodes (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG / UTMASTG = TMA tensor load / store,
+    UTCBAR = tcgen05.commit) and the packed fp32x2 arithmetic of the GELU epilogues (FFMA2), and no
+    legacy HMMA tensor instructions (profiles/r2_sass_histogram.md holds the full histogram)."""
+    import shutil
+    import subprocess
+    from x_clip_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        sass = subprocess.run([exe, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, timeout=300).stdout
+    except (FileNotFoundError, subprocess.TimeoutExpired):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in sass
+    for op, least in (("UTCHMMA", 100), ("LDTM", 50), ("UTMALDG", 50), ("UTMASTG", 10), ("UTCBAR", 20), ("FFMA2", 100)):
+        assert sass.count(op) >= least, (op, sass.count(op))
+    assert sass.count(" HMMA.") == 0
